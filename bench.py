@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the wave-RNN hot path (BASELINE.json metric: Gcell-updates/s = B*Nx*Ny*T / s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+Workload (config.workload = "vowel64"): BASELINE config 3 -- study/example.yml geometry, 150x100 grid, 3 intensity
+probes, synthetic vowel-length waveforms, batch 64 PER GPU (weak scaling), T = 1000, float32.  One "step" is one
+training iteration of wavetorch/train.py:59-72: forward, loss = CrossEntropy(normalize_power(sum_t I)), backward
+(adjoint kernel), all-reduce of the loop gradient over ranks, Adam step on rho, constrain_to_design_region.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: fwd (forward-only throughput), roofline (dominant
+kernel vs the measured HBM copy bandwidth), cpu_baseline (oracle/torch_port.py on the host cores, N=1 only),
+e2e (same step fed from pinned host memory with a device->host read of the loss every step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX, NY, BATCH, T_STEPS = 150, 100, 64, 1000
+METRIC = "Gcell-updates/s, fwd+bwd training step (batch x Nx x Ny x steps / s)"
+UNIT = "Gcell-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="waveforms per GPU")
+    ap.add_argument("--T", type=int, default=T_STEPS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-T", type=int, default=0, help="time steps of the bounded CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def config_dict(args, world):
+    return {"workload": "vowel64", "source": "study/example.yml (BASELINE config 3)", "grid": [NX, NY],
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "time_steps": args.T, "probes": 3,
+            "step": "fwd + CE(normalize_power(sum_t I)) + adjoint + grad all-reduce + Adam + constrain",
+            "parallelism": "batch-sharded x%d" % world,
+            "l2": "no explicit flush: every step writes and re-reads a %.2f GB adjoint tape (>> 126 MB L2)"
+                  % (args.batch * args.T * NX * NY * 4 / 1e9)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference algorithm on the host cores (oracle/torch_port.py)
+# --------------------------------------------------------------------------------------------------
+def cpu_training_throughput(B, T, repeats, warm=True):
+    import numpy as np
+    import torch
+    from oracle import torch_port as tp
+    from oracle import wave_oracle as wo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = wo.vowel_config(np.float32, NX, NY)
+    if warm:
+        tp.time_cpu(cfg, min(B, 8), 10, True)
+    times = []
+    for _ in range(repeats):
+        s, cells = tp.time_cpu(cfg, B, T, True)
+        times.append(s)
+    return cells, times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.batch
+    Tc = args.cpu_T or 100
+    cells, _, cores = cpu_training_throughput(B, Tc, max(args.warmup, 1), warm=True)
+    t0 = time.perf_counter()
+    _, times, _ = cpu_training_throughput(B, Tc, args.steps, warm=False)
+    wall = time.perf_counter() - t0
+    ms = 1e3 * sum(times) / len(times)
+    val = cells / (ms * 1e-3) / 1e9
+    sample = "B=%d, T=%d of %d steps per timed step (throughput per cell-update does not depend on T)" % (B, Tc, args.T)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args, 1),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall,
+            "note": "PyTorch-CPU port of the reference loop (oracle/torch_port.py): the reference is pure Python and "
+                    "does not travel to the GPU box; the port issues the same ATen ops per step"}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def build_model(dev):
+    import torch
+    import wavetorch_b200 as wt
+    N = 20
+    src = wt.WaveSource(N + 20, NY // 2)
+    y0 = int((NY - 40) / 2)
+    probes = [wt.WaveIntensityProbe(NX - N - 20, y0 + 20 * i) for i in range(3)]
+    design = torch.zeros(NX, NY, dtype=torch.uint8)
+    design[src.x.item() + 5:probes[0].x.item() - 5] = 1
+    geom = wt.WaveGeometryFreeForm((NX, NY), 1.4283556979968262, c0=1.0, c1=0.5, eta=0.5, beta=100, abs_sig=3.0,
+                                   abs_N=N, abs_p=4.0, rho="half", blur_radius=1, blur_N=1, design_region=design)
+    return wt.WaveRNN(wt.WaveCell(1.0, geom), [src], probes).to(dev)
+
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import wavetorch_b200 as wt
+    from wavetorch_b200 import _lib
+    from wavetorch_b200.distributed import BatchShardedWaveRNN
+    from oracle import wave_oracle as wo   # synthetic input generator only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, T = args.batch, args.T
+    cells_per_step = B * T * NX * NY
+
+    model = build_model(dev)
+    runner = BatchShardedWaveRNN(model, average=True) if world > 1 else model
+    opt = torch.optim.Adam(model.parameters(), lr=4e-4)
+    x_host = torch.tensor(wo.synthetic_vowels(B, T, first=rank * B)).pin_memory()
+    labels_host = ((torch.arange(B) + rank * B) % 3).pin_memory()
+    x_dev, labels = x_host.to(dev), labels_host.to(dev)
+
+    def train_step(x, y):
+        opt.zero_grad(set_to_none=True)
+        out = runner(x)
+        loss = torch.nn.functional.cross_entropy(wt.utils.normalize_power(out.sum(dim=1)), y)
+        loss.backward()
+        opt.step()
+        model.cell.geom.constrain_to_design_region()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """CUDA-event time of `steps` calls, max over ranks; returns ms per step."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    for _ in range(max(args.warmup, 3)):
+        train_step(x_dev, labels)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    t_wall = time.perf_counter()
+    ms_step = timed(lambda: train_step(x_dev, labels), args.steps)
+    t_wall = time.perf_counter() - t_wall
+    launches = _lib.launch_count - l0
+
+    # end to end: inputs come from pinned host memory, the loss goes back to the host, every step
+    def e2e_step():
+        xb = x_host.to(dev, non_blocking=True)
+        yb = labels_host.to(dev, non_blocking=True)
+        return train_step(xb, yb).item()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # forward only (inference, no tape)
+    def fwd_only():
+        with torch.no_grad():
+            return runner(x_dev) if world == 1 else model(x_dev)
+
+    for _ in range(3):
+        fwd_only()
+    ms_fwd = timed(fwd_only, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # dominant kernels, timed alone with CUDA events on the launching stream
+    out = model(x_dev)
+    loss = torch.nn.functional.cross_entropy(wt.utils.normalize_power(out.sum(dim=1)), labels)
+    (gout,) = torch.autograd.grad(loss, out, retain_graph=True)
+
+    def fwd_tape():
+        return model(x_dev)
+
+    ms_fwd_tape = timed(fwd_tape, max(3, args.steps // 2))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    bw_ms = []
+    for _ in range(max(3, args.steps // 2)):
+        o = model(x_dev)
+        torch.cuda.synchronize()
+        ev[0].record()
+        o.backward(gout)
+        ev[1].record()
+        torch.cuda.synchronize()
+        bw_ms.append(ev[0].elapsed_time(ev[1]))
+        model.zero_grad(set_to_none=True)
+    ms_bwd = statistics.median(bw_ms)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peak_hbm()
+    traffic = ncu_traffic()
+    dom_is_bwd = ms_bwd >= ms_fwd_tape
+    dom_ms = ms_bwd if dom_is_bwd else ms_fwd_tape
+    alg_bytes = 16.0 * cells_per_step        # fwd: read 2 write 1 field + tape write; adjoint: the same in reverse
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    p = _lib.make_problem(NX, NY, B, T, 1, 3, 1.0, 1.4283556979968262, device=local)
+    plan = _lib.query_plan(p)
+    value = world * cells_per_step / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(args, world), "clocks": clocks,
+        "e2e": {"value": world * cells_per_step / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": int(x_host.numel() * 4 + labels_host.numel() * 8), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches,
+        "fwd": {"value": world * cells_per_step / (ms_fwd * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_fwd,
+                "what": "forward only (torch.no_grad, no tape), same workload"},
+        "kernels": {"fwd_with_tape_ms": ms_fwd_tape, "adjoint_ms": ms_bwd, "fwd_no_tape_ms": ms_fwd,
+                    "plan": {"path": "resident" if plan.path == 1 else "stream", "cluster": plan.cluster,
+                             "rows_per_thread": plan.rows_per_thread, "threads": plan.threads,
+                             "clusters": plan.n_clusters, "smem_fwd": plan.smem_fwd, "smem_bwd": plan.smem_bwd}},
+        "roofline": {"bound": "hbm", "kernel": "k_res_adj" if dom_is_bwd else "k_res_fwd", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_cell_update": 16.0, "ms_per_launch": dom_ms,
+                     "traffic": traffic.get("k_res_adj" if dom_is_bwd else "k_res_fwd"),
+                     "note": "fields stay on-chip: algorithmic bytes (3 field passes + 1 tape pass per cell update) "
+                             "are what a non-fused implementation must move; see traffic for the real DRAM bytes"},
+        "roofline_fwd_only": {"achieved": 12.0 * cells_per_step / (ms_fwd * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": 12.0 * cells_per_step / (ms_fwd * 1e-3) / 1e9 / peak,
+                              "algorithmic_bytes_per_cell_update": 12.0},
+        "wall_s_timed_region": t_wall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        Tc = args.cpu_T or 100
+        cells, times, cores = cpu_training_throughput(B, Tc, 2)
+        line["cpu_baseline"] = {"value": cells / min(times) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "B=%d, T=%d of %d steps, fwd+bwd, best of 2 (oracle/torch_port.py)" % (B, Tc, T)}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,160 @@
+/*
+ * wavetorch_b200 -- C ABI of the B200-native wave-RNN hot path.
+ *
+ * This is the drop-in boundary for the time loop of fancompute/wavetorch (reference paths are relative
+ * to the reference repository root):
+ *
+ *   wt_forward        replaces  WaveRNN.forward's Python loop           wavetorch/rnn.py:36-70
+ *                               (WaveCell.forward cell.py:79-107, TimeStep/_time_step cell.py:12-24,
+ *                                _laplacian operators.py:5-11, WaveSource.forward source.py:15-22,
+ *                                WaveProbe/WaveIntensityProbe.forward probe.py:14-27)
+ *   wt_backward       replaces  what autograd replays through the loop: TimeStep.backward cell.py:27-44,
+ *                               the nonlinear b(u), c(u) graph of cell.py:94-102, the source add and the
+ *                               probe gather/square
+ *   wt_step_forward   replaces  TimeStep.forward   (cell.py:22-24)  -- one step, no source/probe
+ *   wt_step_backward  replaces  TimeStep.backward  (cell.py:27-44)
+ *
+ * The reference has no FFI of its own (it is pure Python on ATen); INTEGRATION.md shows the ctypes stub a
+ * maintainer would add to wavetorch/rnn.py and wavetorch/cell.py to bind these entry points.
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless stated otherwise
+ *   - all fields are float32, contiguous, row-major [.., Nx, Ny] with Ny innermost (the reference layout)
+ *   - the caller owns all memory; the library never allocates or frees device memory.  Scratch space is
+ *     sized with wt_query_plan() and passed in
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) of device `device`; calls are
+ *     asynchronous with respect to the host and may be issued concurrently for different devices/streams
+ *   - every entry point returns 0 on success, a negative WT_E* code otherwise; wt_last_error() returns a
+ *     thread-local message.  No exceptions cross the boundary.  There is no CPU fallback.
+ */
+#ifndef WAVETORCH_B200_H
+#define WAVETORCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WT_ABI_VERSION 1
+
+/* status codes */
+#define WT_OK 0
+#define WT_EINVAL (-1)        /* bad argument (shape, null pointer, misaligned, ...) */
+#define WT_ECUDA (-2)         /* a CUDA runtime call failed; see wt_last_error() */
+#define WT_EUNSUPPORTED (-3)  /* valid request that this build cannot run (e.g. device is not sm_100) */
+#define WT_ENOSPACE (-4)      /* history / workspace buffer too small */
+
+/* wt_problem.flags */
+#define WT_F_ZERO_INIT 1u       /* ignore the incoming u1/u2 contents: start from zero fields (rnn.py:39-41) */
+#define WT_F_FORCE_STREAM 2u    /* plan: always use the HBM-streaming kernels                             */
+#define WT_F_FORCE_RESIDENT 4u  /* plan: fail with WT_EUNSUPPORTED instead of falling back to streaming  */
+#define WT_F_NEED_GRAD_B 8u     /* the tape must allow grad w.r.t. the damping field in linear mode      */
+
+/* wt_plan.path */
+#define WT_PATH_STREAM 0    /* one launch per time step, fields live in HBM                     */
+#define WT_PATH_RESIDENT 1  /* whole time loop in one launch, fields live in registers + SMEM   */
+
+/* Problem descriptor (host memory).  dt and h are the values of the reference's `cell.dt` / `geom.h`
+ * buffers; b0, uth, c_nl those of cell.satdamp_b0 / cell.satdamp_uth / cell.c_nl (cell.py:60-64).
+ * Saturable damping is active iff b0 > 0 (cell.py:94); the Kerr term iff c_nl != 0 (cell.py:99). */
+typedef struct wt_problem {
+  int32_t Nx, Ny;   /* grid */
+  int32_t B;        /* independent waveforms (batch) */
+  int32_t T;        /* time steps advanced by this call */
+  int32_t n_src;    /* source pixel entries; a pixel listed k times receives k*x (rnn.py:56-57) */
+  int32_t n_prb;    /* probe pixels */
+  uint32_t flags;
+  int32_t device;   /* CUDA device ordinal */
+  double dt, h;
+  double b0, uth, c_nl;
+  /* tuning overrides, 0 = automatic */
+  int32_t cluster;  /* CTAs per sample (resident path): 1,2,4,8,16 */
+  int32_t rows_per_thread;
+  int32_t reserved[6];
+} wt_problem;
+
+/* What wt_forward/wt_backward will do for a problem, and how much caller-provided scratch they need. */
+typedef struct wt_plan {
+  int32_t path;            /* WT_PATH_* */
+  int32_t cluster;         /* CTAs per sample */
+  int32_t rows_per_thread;
+  int32_t threads;         /* threads per CTA */
+  int32_t rows_per_cta;
+  int32_t n_clusters;      /* clusters in the grid (persistent over samples) */
+  int32_t smem_fwd, smem_bwd;      /* dynamic shared memory per CTA */
+  int32_t nonlinear;       /* bit0 saturable damping, bit1 Kerr */
+  int32_t launches_fwd, launches_bwd; /* kernel launches one call performs */
+  int32_t reserved[5];
+  uint64_t history_bytes;  /* adjoint tape written by wt_forward when `history` is given */
+  uint64_t workspace_fwd_bytes;
+  uint64_t workspace_bwd_bytes;
+} wt_plan;
+
+int wt_abi_version(void);
+const char* wt_last_error(void);
+
+/* Fill `plan` for `p` on p->device (queries the device; launches nothing). */
+int wt_query_plan(const wt_problem* p, wt_plan* plan);
+
+/*
+ * Advance p->T steps for p->B waveforms.
+ *
+ *   c, b        [Nx,Ny]   linear wave speed (geom.c) and damping (geom.b)
+ *   rho         [Nx,Ny]   density fed to the nonlinear terms (geom.rho); may be NULL when linear
+ *   x           [B,T]     input waveforms; x[b,t] is added to every source pixel after step t
+ *   src_ij      [n_src,2] int32 (row, col) of the source pixels
+ *   prb_ij      [n_prb,2] int32 (row, col) of the probe pixels
+ *   prb_square  [n_prb]   int32, nonzero = WaveIntensityProbe (output is the squared field)
+ *   u1, u2      [B,Nx,Ny] in: fields at t-1 and t-2 (ignored with WT_F_ZERO_INIT); out: the two latest fields
+ *   probe_out   [B,T,n_prb] probe readout (squared where prb_square), the reference's model(x) output
+ *   probe_raw   [B,T,n_prb] field at the probes (needed by wt_backward); may be NULL
+ *   fields_out  [B,T,Nx,Ny] every field (output_fields=True, rnn.py:65-67); may be NULL
+ *   history     adjoint tape of plan.history_bytes, or NULL for inference
+ *   workspace   plan.workspace_fwd_bytes
+ */
+int wt_forward(const wt_problem* p, const float* c, const float* b, const float* rho, const float* x,
+               const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, float* u1, float* u2,
+               float* probe_out, float* probe_raw, float* fields_out, void* history, size_t history_bytes,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Reverse-time adjoint of wt_forward over the same p->T steps.
+ *
+ *   grad_probe  [B,T,n_prb]  dLoss/d probe_out
+ *   probe_raw   [B,T,n_prb]  as written by wt_forward
+ *   grad_fields [B,T,Nx,Ny]  dLoss/d fields_out, or NULL
+ *   history     the tape written by wt_forward for the same problem
+ *   adj1, adj2  [B,Nx,Ny]    in/out adjoint state, for chaining segments (zero on the first call; on return
+ *                            adj1 = dLoss/d u1_in, adj2 = dLoss/d u2_in of the matching wt_forward call)
+ *   grad_c, grad_b, grad_rho [Nx,Ny]  OVERWRITTEN with the gradients summed over batch and time
+ *                            (grad_b, grad_rho may be NULL; grad_b in linear mode needs WT_F_NEED_GRAD_B
+ *                            at forward time)
+ *   grad_x      [B,T]        dLoss/dx, or NULL
+ */
+int wt_backward(const wt_problem* p, const float* c, const float* b, const float* rho,
+                const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square,
+                const float* grad_probe, const float* probe_raw, const float* grad_fields,
+                const void* history, size_t history_bytes, float* adj1, float* adj2, float* grad_c,
+                float* grad_b, float* grad_rho, float* grad_x, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/*
+ * One leapfrog step without sources or probes: y = TimeStep.apply(b, c, y1, y2, dt, h).
+ * b and c are [Nx,Ny] (b_batched / c_batched = 0) or [B,Nx,Ny] (= 1).  Uses p->Nx, Ny, B, dt, h, device.
+ */
+int wt_step_forward(const wt_problem* p, const float* b, int b_batched, const float* c, int c_batched,
+                    const float* y1, const float* y2, float* y, void* stream);
+
+/*
+ * TimeStep.backward: per-sample gradients, all [B,Nx,Ny]; any output may be NULL (needs_input_grad = False).
+ */
+int wt_step_backward(const wt_problem* p, const float* b, int b_batched, const float* c, int c_batched,
+                     const float* y1, const float* y2, const float* grad_y, float* grad_b, float* grad_c,
+                     float* grad_y1, float* grad_y2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVETORCH_B200_H */

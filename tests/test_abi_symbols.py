@@ -1,0 +1,53 @@
+"""The C-ABI shared library loads on a machine without a GPU and exports every symbol include/wavetorch_b200.h declares
+(no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "wavetorch_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wt_[a-z_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    names = _declared_functions()
+    for n in ("wt_abi_version", "wt_last_error", "wt_query_plan", "wt_forward", "wt_backward", "wt_step_forward",
+              "wt_step_backward"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    from wavetorch_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in _declared_functions():
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(_lib.EXPORTS) == _declared_functions()
+    lib.wt_abi_version.restype = ctypes.c_int
+    assert lib.wt_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors of wt_problem / wt_plan have the C sizes (8-byte aligned doubles / uint64)."""
+    from wavetorch_b200 import _lib
+    assert ctypes.sizeof(_lib.WtProblem) == 8 * 4 + 5 * 8 + 8 * 4
+    assert ctypes.sizeof(_lib.WtPlan) == 16 * 4 + 3 * 8
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    from wavetorch_b200 import _lib
+    lib = _lib.load()
+    p = _lib.make_problem(0, 10, 1, 1, 0, 0, 1.0, 1.0)
+    plan = _lib.WtPlan()
+    assert lib.wt_query_plan(ctypes.byref(p), ctypes.byref(plan)) == -1
+    assert b"bad grid" in lib.wt_last_error()
+    with pytest.raises(RuntimeError, match="bad grid"):
+        _lib.query_plan(p)

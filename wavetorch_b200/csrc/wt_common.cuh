@@ -1,0 +1,99 @@
+// Shared declarations for the wavetorch_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/wavetorch_b200.h"
+
+namespace wt {
+
+void set_error(const char* fmt, ...);
+
+#define WT_CUDA(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      wt::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return WT_ECUDA;                                                                       \
+    }                                                                                        \
+  } while (0)
+
+#define WT_REQUIRE(cond, ...)          \
+  do {                                 \
+    if (!(cond)) {                     \
+      wt::set_error(__VA_ARGS__);      \
+      return WT_EINVAL;                \
+    }                                  \
+  } while (0)
+
+#define WT_TRY(expr)          \
+  do {                        \
+    int _s = (expr);          \
+    if (_s != WT_OK) return _s; \
+  } while (0)
+
+// Scalars every kernel needs, derived once on the host in double precision.
+struct Scalars {
+  float dt;      // time step
+  float kappa;   // dt^2 / h^2  (the reference multiplies c^2 * h^-2 * stencil, then divides by dt^-2 + b/dt)
+  float b0;      // saturable damping strength (0 = off)
+  float inv_uth; // 1 / uth
+  float c_nl;    // Kerr coefficient (0 = off)
+};
+
+inline Scalars make_scalars(const wt_problem* p) {
+  Scalars s;
+  s.dt = (float)p->dt;
+  s.kappa = (float)((p->dt * p->dt) / (p->h * p->h));
+  s.b0 = (float)p->b0;
+  s.inv_uth = (p->b0 > 0) ? (float)(1.0 / p->uth) : 0.f;
+  s.c_nl = (float)p->c_nl;
+  return s;
+}
+
+inline int nonlinear_mask(const wt_problem* p) { return (p->b0 > 0 ? 1 : 0) | (p->c_nl != 0 ? 2 : 0); }
+
+// ---------------------------------------------------------------------------------------------
+// The cell: per-point arithmetic shared by every kernel (device side).
+//
+// Reference: y = (dt^-2 + b/dt)^-1 * (2/dt^2*y1 - (dt^-2 - b/dt)*y2 + c^2*L_h(y1))   (cell.py:12-17)
+// With beta = b*dt, q = 1/(1+beta), kappa = dt^2/h^2 and L the unscaled 5-point stencil this is
+//     y = 2q*y1 + (1-2q)*y2 + q*kappa*c^2*L(y1)  =  y2 + 2q*(y1 - y2) + (q*kappa*c^2)*L(y1).
+// The last form keeps the y1 and y2 weights summing to exactly one (as the reference's evaluation does
+// in the undamped interior, see oracle/wave_oracle.py:time_step) which matters for float32 drift.
+// ---------------------------------------------------------------------------------------------
+struct CellCoef {
+  float a1;  // 2q
+  float a3;  // q*kappa*c^2
+};
+
+__device__ __forceinline__ float wt_update(float a1, float a3, float u1, float u2, float lap) {
+  return fmaf(a3, lap, fmaf(a1, u1 - u2, u2));
+}
+
+// b(u), c(u) of WaveCell.forward (cell.py:94-102)
+template <bool SAT, bool KERR>
+__device__ __forceinline__ void wt_nl_bc(const Scalars& s, float bpml, float clin, float rho, float u1, float& b,
+                                         float& c, float& d) {
+  d = 1.f;
+  b = bpml;
+  c = clin;
+  if (SAT) {
+    float r = u1 * s.inv_uth;
+    d = fmaf(r, r, 1.f);
+    b = fmaf(rho, s.b0 / d, bpml);
+  }
+  if (KERR) c = fmaf(rho * s.c_nl, u1 * u1, clin);
+}
+
+__device__ __forceinline__ CellCoef wt_coef(const Scalars& s, float b, float c) {
+  float q = 1.f / fmaf(b, s.dt, 1.f);
+  CellCoef k;
+  k.a1 = 2.f * q;
+  k.a3 = q * s.kappa * c * c;
+  return k;
+}
+
+}  // namespace wt

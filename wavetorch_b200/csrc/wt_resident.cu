@@ -1,0 +1,664 @@
+// On-chip ("resident") kernels: the whole time loop of a sample runs in ONE launch.
+//
+// A sample's [Nx,Ny] field is split by rows over a thread-block cluster of C CTAs.  Inside a CTA each thread
+// owns a patch of R rows x 4 columns and keeps, in registers for the whole loop, the two time levels of its
+// cells (u_t, u_{t-1}) and their coefficients.  Shared memory only carries what neighbours need: the current
+// field of the slab (double buffered, with one ghost row per side).  Ghost rows are written straight into
+// the neighbouring CTA's shared memory (DSMEM) and the per-step barrier is the cluster barrier.
+// HBM is touched only for x[b,t], the probe samples, and -- when a gradient is wanted -- the adjoint tape.
+//
+// Forward  : u_{t}   = u_{t-2} + a1*(u_{t-1}-u_{t-2}) + a3*L(u_{t-1}) ; += x[b,t] at sources ; probes read
+// Adjoint  : lam_{t-1} = a1*lam_t + L(a3*lam_t) + (1-a1)*lam_{t+1} + seed_{t-1};  G += L(u_{t-1})*lam_t
+//            (the tape holds L(u_{t-1}) per step in the thread-major order the adjoint reads it back in,
+//             fetched by cp.async.bulk into a shared-memory ring ahead of use)
+//
+// Reference semantics: wavetorch/rnn.py:36-70, cell.py:12-17, cell.py:27-44, operators.py:5-11,
+// source.py:15-22, probe.py:14-27.
+#include <cooperative_groups.h>
+
+#include "wt_common.cuh"
+#include "wt_resident.h"
+#include "wt_stream.h"
+
+namespace cg = cooperative_groups;
+
+namespace wt {
+
+constexpr int TB = 64;        // time steps per x / probe staging block
+constexpr int RING = 4;       // tape prefetch depth (adjoint)
+constexpr int MAX_PRB = 64;   // probes the resident path stages per CTA
+
+struct ResArgs {
+  int Nx, Ny, B, T;
+  int C, Hc, P4, pitch, nact, runs;
+  int n_src, n_prb, n_clusters;
+  unsigned flags;
+  int vec_fields;            // fields_out may be written with float4
+  const float* a1;
+  const float* a3;
+  const float* x;
+  const int32_t* src_ij;
+  const int32_t* prb_ij;
+  const int32_t* prb_sq;
+  float* u1;
+  float* u2;
+  float* probe_out;
+  float* probe_raw;
+  float* fields;
+  float4* tape;
+  // adjoint only
+  const float* grad_probe;
+  float* grad_x;
+  float* Gpart;              // [n_clusters, Nx, Ny]
+  int* status;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WT_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WT_DONE;\n"
+      "bra WT_WAIT;\n"
+      "WT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int R>
+struct Patch {
+  float v[R][4];
+};
+
+// Which of my 4R cells are sources?  m1: listed at least once, m2: listed at least twice (rnn.py:56-57 adds x
+// once per listing).  Three or more listings of one pixel are not supported by this path (status flag).
+template <int R>
+__device__ __forceinline__ void source_masks(const ResArgs& a, bool active, int gi0, int j0, unsigned& m1,
+                                             unsigned& m2) {
+  m1 = 0; m2 = 0;
+  if (!active) return;
+  for (int s = 0; s < a.n_src; ++s) {
+    int si = a.src_ij[2 * s] - gi0, sj = a.src_ij[2 * s + 1] - j0;
+    if (si >= 0 && si < R && sj >= 0 && sj < 4) {
+      unsigned bit = 1u << (si * 4 + sj);
+      if (m1 & bit) {
+        if (m2 & bit) atomicExch(a.status, 1);
+        m2 |= bit;
+      } else {
+        m1 |= bit;
+      }
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void load_coef(const ResArgs& a, bool active, int gi0, int j0, float (&k1)[R][4],
+                                          float (&k3)[R][4]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int gi = gi0 + r, j = j0 + k;
+      bool ok = active && gi < a.Nx && j < a.Ny;
+      k1[r][k] = ok ? a.a1[(size_t)gi * a.Ny + j] : 0.f;
+      k3[r][k] = ok ? a.a3[(size_t)gi * a.Ny + j] : 0.f;
+    }
+}
+
+// Write my R rows into `buf` and, if they border another CTA's slab, into that CTA's ghost row.
+template <int R>
+__device__ __forceinline__ void publish(cg::cluster_group& cluster, const ResArgs& a, float* buf, int rank, int run,
+                                        int lr0, int j0, const float (&v)[R][4]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    *reinterpret_cast<float4*>(buf + (lr0 + r + 1) * a.pitch + 4 + j0) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+  if (a.C > 1) {
+    if (run == 0 && rank > 0) {
+      float* dst = cluster.map_shared_rank(buf + (a.Hc + 1) * a.pitch + 4 + j0, rank - 1);
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+    }
+    if (run == a.runs - 1 && rank < a.C - 1) {
+      float* dst = cluster.map_shared_rank(buf + 4 + j0, rank + 1);
+      *reinterpret_cast<float4*>(dst) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
+    }
+  }
+}
+
+// Unscaled 5-point Laplacian of my patch; own cells come from registers, the rim from shared memory.
+template <int R>
+__device__ __forceinline__ void patch_laplacian(const ResArgs& a, const float* buf, int lr0, int j0,
+                                                const float (&v)[R][4], float (&lap)[R][4]) {
+  const float4 up = *reinterpret_cast<const float4*>(buf + lr0 * a.pitch + 4 + j0);
+  const float4 dn = *reinterpret_cast<const float4*>(buf + (lr0 + R + 1) * a.pitch + 4 + j0);
+  const float upv[4] = {up.x, up.y, up.z, up.w};
+  const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float* row = buf + (lr0 + r + 1) * a.pitch + 4 + j0;
+    const float lf = row[-1], rt = row[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float n = (r == 0) ? upv[k] : v[r - 1][k];
+      float s = (r == R - 1) ? dnv[k] : v[r + 1][k];
+      float w = (k == 0) ? lf : v[r][k - 1];
+      float e = (k == 3) ? rt : v[r][k + 1];
+      lap[r][k] = fmaf(-4.f, v[r][k], (n + s) + (w + e));
+    }
+  }
+}
+
+template <int R>
+constexpr int res_max_threads() {
+  return R <= 2 ? 1024 : R == 3 ? 768 : R <= 5 ? 512 : R == 6 ? 384 : 256;
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int R>
+__global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (a.C > 1) ? (int)cluster.block_rank() : 0;
+  const int cid = blockIdx.x / a.C;
+  const int tid = threadIdx.x;
+  const bool active = tid < a.nact;
+  const int run = tid / a.P4;
+  const int j0 = 4 * (tid - run * a.P4);
+  const int lr0 = run * R;
+  const int gi0 = rank * a.Hc + lr0;
+  const int slab = (a.Hc + 2) * a.pitch;
+
+  extern __shared__ float4 smem4[];
+  float* fld = reinterpret_cast<float*>(smem4);       // [2][slab]
+  float* xs = fld + 2 * slab;                          // [2][TB]
+  float* ps = xs + 2 * TB;                             // [2][TB][n_prb]
+  int* poff = reinterpret_cast<int*>(ps + 2 * TB * a.n_prb);  // [n_prb] offset into a slab buffer, or -1
+
+  float k1[R][4], k3[R][4];
+  load_coef<R>(a, active, gi0, j0, k1, k3);
+  unsigned m1, m2;
+  source_masks<R>(a, active, gi0, j0, m1, m2);
+  for (int p = tid; p < a.n_prb; p += blockDim.x) {
+    int li = a.prb_ij[2 * p] - rank * a.Hc, pj = a.prb_ij[2 * p + 1];
+    poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * a.pitch + 4 + pj : -1;
+  }
+  for (int i = tid; i < 2 * slab; i += blockDim.x) fld[i] = 0.f;
+  auto sync = [&]() {
+    if (a.C > 1) cluster.sync(); else __syncthreads();
+  };
+  sync();
+
+  for (int b = cid; b < a.B; b += a.n_clusters) {
+    float v[R][4], w[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int gi = gi0 + r, j = j0 + k;
+        bool ok = active && gi < a.Nx && j < a.Ny && !(a.flags & WT_F_ZERO_INIT);
+        size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
+        v[r][k] = ok ? a.u1[o] : 0.f;
+        w[r][k] = ok ? a.u2[o] : 0.f;
+      }
+    if (active) publish<R>(cluster, a, fld, rank, run, lr0, j0, v);
+    const float* xb = a.x + (size_t)b * a.T;
+    for (int i = tid; i < TB && i < a.T; i += blockDim.x) xs[i] = xb[i];
+    sync();
+
+    int flushed = 0;
+    auto flush = [&](int blk) {   // probe samples of time block blk -> HBM
+      const int t0 = blk * TB, n = min(TB, a.T - t0);
+      const float* src = ps + (blk & 1) * TB * a.n_prb;
+      for (int i = tid; i < n * a.n_prb; i += blockDim.x) {
+        int p = i % a.n_prb;
+        if (poff[p] >= 0) {
+          float val = src[i];
+          size_t o = ((size_t)b * a.T + t0 + i / a.n_prb) * a.n_prb + p;
+          if (a.probe_raw) a.probe_raw[o] = val;
+          if (a.probe_out) a.probe_out[o] = a.prb_sq[p] ? val * val : val;
+        }
+      }
+    };
+    auto record = [&](const float* buf, int t) {   // sample the probes of step t from the slab buffer holding u_t
+      if (tid < a.n_prb && poff[tid] >= 0) ps[((t / TB) & 1) * TB * a.n_prb + (t % TB) * a.n_prb + tid] = buf[poff[tid]];
+    };
+
+    for (int t = 0; t < a.T; ++t) {
+      const float* cur = fld + (t & 1) * slab;
+      float* nxt = fld + ((t + 1) & 1) * slab;
+      const int blk = t / TB, tt = t - blk * TB;
+      if (tt == 0 && (blk + 1) * TB < a.T) {   // stage the next block of x
+        float* dst = xs + ((blk + 1) & 1) * TB;
+        const int t1 = (blk + 1) * TB;
+        for (int i = tid; i < TB && t1 + i < a.T; i += blockDim.x) dst[i] = xb[t1 + i];
+      }
+      if (t > 0) {
+        record(cur, t - 1);
+        if (t - 1 >= (flushed + 1) * TB) { flush(flushed); ++flushed; }
+      }
+      if (active) {
+        float lap[R][4];
+        patch_laplacian<R>(a, cur, lr0, j0, v, lap);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float y = wt_update(k1[r][k], k3[r][k], v[r][k], w[r][k], lap[r][k]);
+            w[r][k] = v[r][k];
+            v[r][k] = y;
+          }
+        if (m1) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t]
+          const float xv = xs[(blk & 1) * TB + tt];
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (m1 >> (r * 4 + k) & 1u) v[r][k] += xv;
+              if (m2 >> (r * 4 + k) & 1u) v[r][k] += xv;
+            }
+        }
+        publish<R>(cluster, a, nxt, rank, run, lr0, j0, v);
+        if (a.tape) {
+          float4* tp = a.tape + ((((size_t)b * a.T + t) * a.C + rank) * R) * blockDim.x + tid;
+#pragma unroll
+          for (int r = 0; r < R; ++r) st_stream(tp + (size_t)r * blockDim.x, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
+        }
+        if (a.fields) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            int gi = gi0 + r;
+            if (gi < a.Nx) {
+              float* f = a.fields + (((size_t)b * a.T + t) * a.Nx + gi) * a.Ny + j0;
+              if (a.vec_fields) {
+                *reinterpret_cast<float4*>(f) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (j0 + k < a.Ny) f[k] = v[r][k];
+              }
+            }
+          }
+        }
+      }
+      sync();
+    }
+    record(fld + (a.T & 1) * slab, a.T - 1);
+    __syncthreads();
+    while (flushed * TB < a.T) { flush(flushed); ++flushed; }
+    // final state back to HBM: u1 = latest field, u2 = the one before (cell.py:107)
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int gi = gi0 + r, j = j0 + k;
+        if (active && gi < a.Nx && j < a.Ny) {
+          size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
+          a.u1[o] = v[r][k];
+          a.u2[o] = w[r][k];
+        }
+      }
+    sync();   // nobody may publish the next sample's initial field while a neighbour still reads this one
+  }
+}
+
+// =================================================================================================
+// adjoint
+// =================================================================================================
+template <int R>
+__global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (a.C > 1) ? (int)cluster.block_rank() : 0;
+  const int cid = blockIdx.x / a.C;
+  const int tid = threadIdx.x;
+  const bool active = tid < a.nact;
+  const int run = tid / a.P4;
+  const int j0 = 4 * (tid - run * a.P4);
+  const int lr0 = run * R;
+  const int gi0 = rank * a.Hc + lr0;
+  const int slab = (a.Hc + 2) * a.pitch;
+  const int NT = blockDim.x;
+  const unsigned stage_bytes = (unsigned)(R * NT * sizeof(float4));
+
+  extern __shared__ float4 smem4[];
+  float4* ring = smem4;                                        // [RING][R*NT]
+  float* fld = reinterpret_cast<float*>(ring + RING * R * NT);  // [2][slab]   P = a3*lambda
+  float* ss = fld + 2 * slab;                                   // [2][TB][n_prb] probe seeds
+  float* gxs = ss + 2 * TB * a.n_prb;                           // [2][TB]     dLoss/dx staging
+  int* pown = reinterpret_cast<int*>(gxs + 2 * TB);             // [n_prb] owning thread, or -1
+  int* pcell = pown + a.n_prb;                                  // [n_prb] cell index inside the owner's patch
+  uint64_t* full = reinterpret_cast<uint64_t*>(pcell + a.n_prb + ((2 * a.n_prb) & 1));  // [RING], 8-byte aligned
+
+  float k1[R][4], k3[R][4];
+  load_coef<R>(a, active, gi0, j0, k1, k3);
+  unsigned m1, m2;
+  source_masks<R>(a, active, gi0, j0, m1, m2);
+  for (int p = tid; p < a.n_prb; p += NT) {
+    int li = a.prb_ij[2 * p] - rank * a.Hc, pj = a.prb_ij[2 * p + 1];
+    bool mine = li >= 0 && li < a.Hc;
+    pown[p] = mine ? (li / R) * a.P4 + pj / 4 : -1;
+    pcell[p] = mine ? (li % R) * 4 + (pj & 3) : 0;
+  }
+  for (int i = tid; i < 2 * slab; i += NT) fld[i] = 0.f;
+  for (int i = tid; i < 2 * TB; i += NT) gxs[i] = 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < RING; ++s) mbar_init(full + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  auto sync = [&]() {
+    if (a.C > 1) cluster.sync(); else __syncthreads();
+  };
+  sync();
+  bool has_probe = false;
+  for (int p = 0; p < a.n_prb; ++p) has_probe |= (pown[p] == tid);
+
+  float G[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) G[r][k] = 0.f;
+
+  unsigned it_global = 0;   // tape stages consumed so far (ring slot / parity bookkeeping across samples)
+  for (int b = cid; b < a.B; b += a.n_clusters) {
+    float lam[R][4], c2[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { lam[r][k] = 0.f; c2[r][k] = 0.f; }
+
+    auto tape_ptr = [&](int t) { return a.tape + ((((size_t)b * a.T + t) * a.C + rank) * R) * NT; };
+    auto stage_seeds = [&](int blk) {   // seeds of time block blk: dLoss/d(raw probe value)
+      const int t0 = blk * TB, n = min(TB, a.T - t0);
+      float* dst = ss + (blk & 1) * TB * a.n_prb;
+      for (int i = tid; i < n * a.n_prb; i += NT) {
+        int p = i % a.n_prb;
+        size_t o = ((size_t)b * a.T + t0 + i / a.n_prb) * a.n_prb + p;
+        float g = a.grad_probe[o];
+        if (a.prb_sq[p]) g *= 2.f * a.probe_raw[o];   // probe.py:27
+        dst[i] = g;
+      }
+    };
+    auto flush_gx = [&](int blk) {
+      const int t0 = blk * TB, n = min(TB, a.T - t0);
+      float* src = gxs + (blk & 1) * TB;
+      for (int i = tid; i < n; i += NT) {
+        float s = src[i];
+        src[i] = 0.f;
+        if (s != 0.f) atomicAdd(a.grad_x + (size_t)b * a.T + t0 + i, s);
+      }
+    };
+    if (tid == 0) {   // prime the tape ring
+      for (int s = 0; s < RING && s < a.T; ++s) {
+        unsigned slot = (it_global + s) % RING;
+        mbar_expect_tx(full + slot, stage_bytes);
+        bulk_g2s(ring + slot * R * NT, tape_ptr(a.T - 1 - s), stage_bytes, full + slot);
+      }
+    }
+    stage_seeds((a.T - 1) / TB);
+    sync();
+
+    for (int t = a.T - 1, it = 0; t >= 0; --t, ++it) {
+      const int blk = t / TB, tt = t - blk * TB;
+      float* cur = fld + (it & 1) * slab;
+      if ((t == a.T - 1 || tt == TB - 1) && blk > 0) stage_seeds(blk - 1);
+      if (a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
+      const unsigned slot = (it_global + it) % RING, parity = ((it_global + it) / RING) & 1u;
+      float pv[R][4];
+      if (active) {
+        if (has_probe) {   // lambda_t += dLoss/du_t through the probes
+          for (int p = 0; p < a.n_prb; ++p)
+            if (pown[p] == tid) {
+              const float sv = ss[(blk & 1) * TB * a.n_prb + tt * a.n_prb + p];
+              const int pc = pcell[p];
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (pc == r * 4 + k) lam[r][k] += sv;
+            }
+        }
+        if (a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t
+          float s = 0.f;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (m1 >> (r * 4 + k) & 1u) s += lam[r][k];
+              if (m2 >> (r * 4 + k) & 1u) s += lam[r][k];
+            }
+          atomicAdd(gxs + (blk & 1) * TB + tt, s);
+        }
+        mbar_wait(full + slot, parity);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 l = ring[slot * R * NT + r * NT + tid];
+          const float lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            G[r][k] = fmaf(lv[k], lam[r][k], G[r][k]);     // cell.py:36, scaled once at the end
+            pv[r][k] = k3[r][k] * lam[r][k];
+          }
+        }
+        publish<R>(cluster, a, cur, rank, run, lr0, j0, pv);
+      }
+      sync();
+      if (active) {
+        float lapP[R][4];
+        patch_laplacian<R>(a, cur, lr0, j0, pv, lapP);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float nl = c2[r][k] + fmaf(k1[r][k], lam[r][k], lapP[r][k]);   // cell.py:39-40
+            c2[r][k] = (1.f - k1[r][k]) * lam[r][k];                        // cell.py:42
+            lam[r][k] = nl;
+          }
+      }
+      if (tid == 0 && it + RING < a.T) {   // every thread passed the barrier after reading this slot: refill it
+        mbar_expect_tx(full + slot, stage_bytes);
+        bulk_g2s(ring + slot * R * NT, tape_ptr(t - RING), stage_bytes, full + slot);
+      }
+    }
+    it_global += (unsigned)a.T;
+    sync();
+    if (a.grad_x) { flush_gx(0); }
+    sync();
+  }
+  // per-cluster partial of sum_{b,t} L(u_{t-1})*lambda_t ; reduced and scaled by k_finish_grad
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int gi = gi0 + r, j = j0 + k;
+      if (active && gi < a.Nx && j < a.Ny) a.Gpart[((size_t)cid * a.Nx + gi) * a.Ny + j] = G[r][k];
+    }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static size_t smem_fwd_bytes(int Hc, int pitch, int n_prb) {
+  return (size_t)2 * (Hc + 2) * pitch * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)n_prb * 4 + 16;
+}
+static size_t smem_adj_bytes(int Hc, int pitch, int n_prb, int R, int threads) {
+  return (size_t)RING * R * threads * 16 + (size_t)2 * (Hc + 2) * pitch * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
+         (size_t)2 * n_prb * 4 + 8 + RING * 8 + 16;
+}
+
+static int max_threads_for(int R) {
+  switch (R) {
+    case 1: case 2: return 1024;
+    case 3: return 768;
+    case 4: case 5: return 512;
+    case 6: return 384;
+    case 8: return 256;
+    default: return 0;
+  }
+}
+
+bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_adjoint, wt_plan* plan) {
+  if (nonlinear_mask(p) || (p->flags & WT_F_NEED_GRAD_B)) return false;
+  if (p->n_prb > MAX_PRB || p->T < 1) return false;
+  const int P4 = (p->Ny + 3) / 4, pitch = 4 * P4 + 4;
+  const int smem_cap = (int)prop.sharedMemPerBlockOptin;
+  static const int Rs[] = {8, 6, 5, 4, 3, 2, 1};
+  static const int Cs[] = {1, 2, 4, 8, 16};
+  int bestC = 0, bestR = 0;
+  double best_score = -1;
+  for (int C : Cs) {
+    if (p->cluster && C != p->cluster) continue;
+    if (C > 8 && !p->cluster) continue;   // non-portable cluster sizes only on request
+    for (int R : Rs) {
+      if (p->rows_per_thread && R != p->rows_per_thread) continue;
+      const int Hc = round_up((p->Nx + C - 1) / C, R);
+      if ((C - 1) * Hc >= p->Nx) continue;            // every CTA must own at least one real row
+      const int runs = Hc / R, nact = runs * P4, threads = round_up(nact, 32);
+      if (threads > max_threads_for(R)) continue;
+      size_t sm = need_adjoint ? smem_adj_bytes(Hc, pitch, p->n_prb, R, threads) : smem_fwd_bytes(Hc, pitch, p->n_prb);
+      if ((int)sm > smem_cap) continue;
+      // score: SMs kept busy x work per thread efficiency (bigger patches amortise the rim reads)
+      const double ctas = (double)p->B * C;
+      const double waves = ctas / prop.multiProcessorCount;
+      const double busy = waves <= 1.0 ? waves : waves / (double)((long)waves + (waves > (long)waves ? 1 : 0));
+      const double rim = (double)(4 * R) / (4 * R + 2 * R + 8);   // own cells / (own + rim loads)
+      const double lane = (double)nact / threads;
+      const double sync_cost = C > 1 ? 0.85 : 1.0;
+      const double par = threads >= 256 ? 1.0 : threads / 256.0;
+      const double score = busy * rim * lane * sync_cost * par;
+      if (score > best_score) { best_score = score; bestC = C; bestR = R; }
+    }
+  }
+  if (!bestC) return false;
+  const int Hc = round_up((p->Nx + bestC - 1) / bestC, bestR);
+  const int runs = Hc / bestR, nact = runs * P4, threads = round_up(nact, 32);
+  plan->path = WT_PATH_RESIDENT;
+  plan->cluster = bestC;
+  plan->rows_per_thread = bestR;
+  plan->threads = threads;
+  plan->rows_per_cta = Hc;
+  int ncl = prop.multiProcessorCount / bestC;
+  if (ncl < 1) ncl = 1;
+  plan->n_clusters = p->B < ncl ? p->B : ncl;
+  plan->smem_fwd = (int)smem_fwd_bytes(Hc, pitch, p->n_prb);
+  plan->smem_bwd = (int)smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads);
+  plan->history_bytes = (uint64_t)p->B * p->T * bestC * bestR * threads * 16;
+  const size_t plane = (size_t)p->Nx * p->Ny;
+  plan->workspace_fwd_bytes = 3 * plane * 4 + 64;
+  plan->workspace_bwd_bytes = (3 + (size_t)plan->n_clusters) * plane * 4 + 64;
+  plan->launches_fwd = 2;
+  plan->launches_bwd = 3;
+  return true;
+}
+
+static void fill_args(const wt_problem* p, const wt_plan& plan, ResArgs* a) {
+  a->Nx = p->Nx; a->Ny = p->Ny; a->B = p->B; a->T = p->T;
+  a->C = plan.cluster; a->Hc = plan.rows_per_cta; a->P4 = (p->Ny + 3) / 4; a->pitch = 4 * a->P4 + 4;
+  a->runs = plan.rows_per_cta / plan.rows_per_thread; a->nact = a->runs * a->P4;
+  a->n_src = p->n_src; a->n_prb = p->n_prb; a->n_clusters = plan.n_clusters; a->flags = p->flags;
+}
+
+template <typename K>
+static int launch_cluster(K kernel, const wt_plan& plan, size_t smem, const ResArgs& a, cudaStream_t st) {
+  WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (plan.cluster > 8) WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.n_clusters * plan.cluster);
+  cfg.blockDim = dim3(plan.threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WT_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
+  return WT_OK;
+}
+
+#define WT_DISPATCH_R(R_, CALL)                  \
+  switch (R_) {                                  \
+    case 1: { constexpr int R = 1; CALL; } break; \
+    case 2: { constexpr int R = 2; CALL; } break; \
+    case 3: { constexpr int R = 3; CALL; } break; \
+    case 4: { constexpr int R = 4; CALL; } break; \
+    case 5: { constexpr int R = 5; CALL; } break; \
+    case 6: { constexpr int R = 6; CALL; } break; \
+    case 8: { constexpr int R = 8; CALL; } break; \
+    default: wt::set_error("rows_per_thread=%d not instantiated", R_); return WT_EINVAL; \
+  }
+
+int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, const float* b, const float* x,
+                     const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_sq, float* u1, float* u2,
+                     float* probe_out, float* probe_raw, float* fields_out, void* history, void* workspace,
+                     cudaStream_t st) {
+  const size_t plane = (size_t)p->Nx * p->Ny;
+  float* a1 = reinterpret_cast<float*>(workspace);
+  float* a3 = a1 + plane;
+  float* gs = a3 + plane;
+  int* status = reinterpret_cast<int*>(gs + plane);
+  k_coeff<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(b, c, (int)plane, p->dt, (p->dt * p->dt) / (p->h * p->h), a1,
+                                                            a3, gs);
+  WT_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  ResArgs a = {};
+  fill_args(p, plan, &a);
+  a.a1 = a1; a.a3 = a3; a.x = x; a.src_ij = src_ij; a.prb_ij = prb_ij; a.prb_sq = prb_sq;
+  a.u1 = u1; a.u2 = u2; a.probe_out = probe_out; a.probe_raw = probe_raw; a.fields = fields_out;
+  a.vec_fields = (p->Ny % 4 == 0) && (((uintptr_t)fields_out & 15) == 0);
+  a.tape = reinterpret_cast<float4*>(history);
+  a.status = status;
+  WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R>, plan, plan.smem_fwd, a, st)));
+  return WT_OK;
+}
+
+int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, const float* b, const int32_t* src_ij,
+                      const int32_t* prb_ij, const int32_t* prb_sq, const float* grad_probe, const float* probe_raw,
+                      const void* history, float* grad_c, float* grad_b, float* grad_rho, float* grad_x,
+                      void* workspace, cudaStream_t st) {
+  const size_t plane = (size_t)p->Nx * p->Ny;
+  float* a1 = reinterpret_cast<float*>(workspace);
+  float* a3 = a1 + plane;
+  float* gs = a3 + plane;
+  float* Gpart = gs + plane;
+  int* status = reinterpret_cast<int*>(Gpart + (size_t)plan.n_clusters * plane);
+  k_coeff<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(b, c, (int)plane, p->dt, (p->dt * p->dt) / (p->h * p->h), a1,
+                                                            a3, gs);
+  WT_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  if (grad_x) WT_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)p->B * p->T * sizeof(float), st));
+  ResArgs a = {};
+  fill_args(p, plan, &a);
+  a.a1 = a1; a.a3 = a3; a.src_ij = src_ij; a.prb_ij = prb_ij; a.prb_sq = prb_sq;
+  a.probe_raw = const_cast<float*>(probe_raw); a.grad_probe = grad_probe; a.grad_x = grad_x;
+  a.tape = reinterpret_cast<float4*>(const_cast<void*>(history));
+  a.Gpart = Gpart; a.status = status;
+  WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st)));
+  k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gpart, gs, plan.n_clusters, plane, grad_c);
+  if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
+  if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));
+  WT_CUDA(cudaGetLastError());
+  return WT_OK;
+}
+
+}  // namespace wt

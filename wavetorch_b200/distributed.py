@@ -1,0 +1,92 @@
+"""Batch sharding across the GPUs of one box (one process per GPU, torch.distributed over NCCL/NVLink).
+
+The reference has no distributed code.  Waveforms are independent (rnn.py:36-41: per-sample
+state, shared geometry), so the batch is split contiguously over ranks with the geometry replicated and the
+only collective is ONE all-reduce of the gradient that leaves the time loop -- dLoss/dc, plus the direct
+dLoss/drho of the nonlinear terms -- issued on the adjoint's stream right after wt_backward.  Reducing before
+the geometry chain (blur/projection backward) gives the same rho.grad on every rank as reducing after it,
+because that chain is linear in the incoming gradient.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous [lo, hi) slice of n samples owned by `rank`; the first n % world_size ranks get one more."""
+    base, extra = divmod(int(n), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(x, group=None, dim=0):
+    """This rank's contiguous slice of a batch-first tensor."""
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(x.shape[dim], ws, rk)
+    return x.narrow(dim, lo, hi - lo)
+
+
+class _SumGradAcrossRanks(torch.autograd.Function):
+    """Identity in forward; all-reduce(sum) of the incoming gradients in backward, as one fused buffer."""
+
+    @staticmethod
+    def forward(ctx, group, scale, *tensors):
+        ctx.group, ctx.scale = group, scale
+        return tuple(t.view_as(t) for t in tensors)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        live = [g for g in grads if g is not None]
+        if live:
+            flat = torch.cat([g.reshape(-1).to(torch.float32) for g in live])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=ctx.group)
+            if ctx.scale != 1.0:
+                flat.mul_(ctx.scale)
+            out, o = [], 0
+            for g in grads:
+                if g is None:
+                    out.append(None)
+                else:
+                    n = g.numel()
+                    out.append(flat[o:o + n].view_as(g).to(g.dtype))
+                    o += n
+        else:
+            out = list(grads)
+        return (None, None) + tuple(out)
+
+
+def sync_grads(*tensors, group=None, average=False):
+    """Return views of `tensors` whose gradients are summed (or averaged) over all ranks in backward."""
+    scale = 1.0 / dist.get_world_size(group) if average else 1.0
+    return _SumGradAcrossRanks.apply(group, scale, *tensors)
+
+
+class BatchShardedWaveRNN(torch.nn.Module):
+    """Wraps a WaveRNN: forward takes this rank's shard of the waveforms; in backward the loop gradients
+    (dLoss/dc and the direct dLoss/drho) are all-reduced once, so `rho.grad` is the gradient of the SUM of the
+    per-rank losses (pass average=True for the mean) on every rank."""
+
+    def __init__(self, model, group=None, average=False):
+        super().__init__()
+        self.model = model
+        self.group = group
+        self.average = average
+
+    def forward(self, x_local, output_fields=False):
+        from .functional import LoopSpec, wave_rnn  # noqa: F401
+        m = self.model
+        geom = m.cell.geom
+        c, rho, b = geom.c, geom.rho, geom.b
+        nonlinear = m.cell.host_scalars()["b0"] > 0 or m.cell.host_scalars()["c_nl"] != 0
+        if torch.is_grad_enabled() and (c.requires_grad or (nonlinear and rho.requires_grad)):
+            if nonlinear:
+                c, rho = sync_grads(c, rho, group=self.group, average=self.average)
+            else:
+                (c,) = sync_grads(c, group=self.group, average=self.average)
+        return m._run(x_local, c, b, rho, output_fields)
+
+    def gather_outputs(self, y_local):
+        """All-gather the per-rank outputs along the batch axis (equal shard sizes required)."""
+        ws = dist.get_world_size(self.group)
+        parts = [torch.empty_like(y_local) for _ in range(ws)]
+        dist.all_gather(parts, y_local.contiguous(), group=self.group)
+        return torch.cat(parts, dim=0)

@@ -1,0 +1,191 @@
+"""autograd.Function wrappers around the C ABI: the whole WaveRNN time loop and the single TimeStep.
+
+`wave_rnn` replaces the Python loop of wavetorch/rnn.py:50-70 with one call to wt_forward (and one call to
+wt_backward when a gradient is requested).  `time_step` is the drop-in for TimeStep.apply (cell.py:20-44).
+"""
+import ctypes
+import warnings
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+_warned_f64 = False
+
+
+def _f32(t, name):
+    """The kernels compute in float32 (BASELINE north star); float64 inputs are cast with one warning."""
+    global _warned_f64
+    if t is None:
+        return None
+    if t.dtype == torch.float64 and not _warned_f64:
+        warnings.warn("wavetorch_b200: the CUDA time loop computes in float32; float64 %s is cast" % name)
+        _warned_f64 = True
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "wavetorch_b200: %s lives on %s. The wave-RNN hot path has no CPU fallback; move the model and the "
+            "inputs to a CUDA device (model.to('cuda'), x.cuda())." % (what, t.device))
+
+
+@dataclass
+class LoopSpec:
+    """Static description of one WaveRNN forward: everything that is not a differentiable tensor."""
+    src_ij: torch.Tensor      # int32 [n_src, 2] on the device
+    prb_ij: torch.Tensor      # int32 [n_prb, 2]
+    prb_sq: torch.Tensor      # int32 [n_prb]
+    dt: float
+    h: float
+    b0: float = 0.0
+    uth: float = 0.0
+    c_nl: float = 0.0
+    output_fields: bool = False
+    flags: int = 0
+    cluster: int = 0
+    rows_per_thread: int = 0
+
+
+class _WaveLoop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, c, b, rho, spec):
+        lib = _lib.load()
+        _require_cuda(x, "the input waveform x")
+        _require_cuda(c, "the wave speed c")
+        dev = x.device
+        out_dtype = x.dtype
+        x32, c32, b32, rho32 = _f32(x, "x"), _f32(c, "c"), _f32(b, "b"), _f32(rho, "rho")
+        B, T = x32.shape
+        Nx, Ny = c32.shape
+        need = ctx.needs_input_grad
+        want_grad = any(need[:4]) and T > 0
+        flags = spec.flags | _lib.WT_F_ZERO_INIT
+        if need[2]:
+            flags |= _lib.WT_F_NEED_GRAD_B
+        if spec.output_fields and want_grad:
+            flags |= _lib.WT_F_FORCE_STREAM     # dLoss/dfields is implemented by the streaming adjoint
+        n_src, n_prb = spec.src_ij.shape[0], spec.prb_ij.shape[0]
+        prob = _lib.make_problem(Nx, Ny, B, T, n_src, n_prb, spec.dt, spec.h, spec.b0, spec.uth, spec.c_nl, flags,
+                                 dev.index if dev.index is not None else torch.cuda.current_device(), spec.cluster,
+                                 spec.rows_per_thread)
+        plan = _lib.query_plan(prob)
+        u1 = torch.empty((B, Nx, Ny), device=dev, dtype=torch.float32)
+        u2 = torch.empty((B, Nx, Ny), device=dev, dtype=torch.float32)
+        probe_out = torch.empty((B, T, n_prb), device=dev, dtype=torch.float32)
+        probe_raw = torch.empty((B, T, n_prb), device=dev, dtype=torch.float32) if want_grad else None
+        fields = torch.empty((B, T, Nx, Ny), device=dev, dtype=torch.float32) if spec.output_fields else None
+        ws = torch.empty(max(int(plan.workspace_fwd_bytes), 16), device=dev, dtype=torch.uint8)
+        hist = torch.empty(max(int(plan.history_bytes), 16), device=dev, dtype=torch.uint8) if want_grad else None
+        with torch.cuda.device(dev):
+            st = lib.wt_forward(ctypes.byref(prob), _lib.ptr(c32), _lib.ptr(b32), _lib.ptr(rho32), _lib.ptr(x32),
+                                _lib.ptr(spec.src_ij), _lib.ptr(spec.prb_ij), _lib.ptr(spec.prb_sq), _lib.ptr(u1),
+                                _lib.ptr(u2), _lib.ptr(probe_out), _lib.ptr(probe_raw), _lib.ptr(fields),
+                                _lib.ptr(hist), hist.numel() if hist is not None else 0, _lib.ptr(ws), ws.numel(),
+                                _lib.stream_ptr(dev))
+        _lib.check(st, "wt_forward")
+        _lib.count_launches(plan.launches_fwd)
+        if want_grad:
+            ctx.prob, ctx.plan, ctx.spec = prob, plan, spec
+            ctx.saved = (c32, b32, rho32, probe_raw, hist)
+            ctx.dtypes = (x.dtype, c.dtype, b.dtype, rho.dtype if rho is not None else None)
+        result = fields if spec.output_fields else probe_out
+        return result.to(out_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        prob, plan, spec = ctx.prob, ctx.plan, ctx.spec
+        c32, b32, rho32, probe_raw, hist = ctx.saved
+        dev = c32.device
+        B, T, Nx, Ny = prob.B, prob.T, prob.Nx, prob.Ny
+        need = ctx.needs_input_grad
+        g = grad_out.detach().to(torch.float32).contiguous()
+        if spec.output_fields:
+            grad_fields, grad_probe = g, torch.zeros((B, T, prob.n_prb), device=dev, dtype=torch.float32)
+        else:
+            grad_fields, grad_probe = None, g
+        grad_c = torch.empty((Nx, Ny), device=dev, dtype=torch.float32)
+        grad_b = torch.empty((Nx, Ny), device=dev, dtype=torch.float32) if need[2] else None
+        grad_rho = torch.empty((Nx, Ny), device=dev, dtype=torch.float32) if (need[3] and plan.nonlinear) else None
+        grad_x = torch.empty((B, T), device=dev, dtype=torch.float32) if need[0] else None
+        ws = torch.empty(max(int(plan.workspace_bwd_bytes), 16), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            st = lib.wt_backward(ctypes.byref(prob), _lib.ptr(c32), _lib.ptr(b32), _lib.ptr(rho32),
+                                 _lib.ptr(spec.src_ij), _lib.ptr(spec.prb_ij), _lib.ptr(spec.prb_sq),
+                                 _lib.ptr(grad_probe), _lib.ptr(probe_raw), _lib.ptr(grad_fields), _lib.ptr(hist),
+                                 hist.numel(), None, None, _lib.ptr(grad_c), _lib.ptr(grad_b), _lib.ptr(grad_rho),
+                                 _lib.ptr(grad_x), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(st, "wt_backward")
+        _lib.count_launches(plan.launches_bwd)
+        ctx.saved = None
+        xd, cd, bd, rd = ctx.dtypes
+        if need[3] and grad_rho is None:
+            grad_rho = torch.zeros((Nx, Ny), device=dev, dtype=torch.float32)   # linear: rho does not enter the loop
+        return (grad_x.to(xd) if need[0] else None, grad_c.to(cd) if need[1] else None,
+                grad_b.to(bd) if need[2] else None, grad_rho.to(rd) if need[3] else None, None)
+
+
+def wave_rnn(x, c, b, rho, spec):
+    """Run the fused time loop.  x [B,T]; c, b, rho [Nx,Ny]; returns [B,T,n_prb] (or [B,T,Nx,Ny])."""
+    return _WaveLoop.apply(x, c, b, rho, spec)
+
+
+class TimeStep(torch.autograd.Function):
+    """Drop-in for wavetorch.cell.TimeStep (cell.py:20-44): y = TimeStep.apply(b, c, y1, y2, dt, h)."""
+
+    @staticmethod
+    def forward(ctx, b, c, y1, y2, dt, h):
+        lib = _lib.load()
+        _require_cuda(y1, "the field y1")
+        dev = y1.device
+        B, Nx, Ny = y1.shape
+        b32, c32, y132, y232 = (_f32(t, n) for t, n in ((b, "b"), (c, "c"), (y1, "y1"), (y2, "y2")))
+        for t, n in ((b32, "b"), (c32, "c")):
+            if tuple(t.shape) not in ((Nx, Ny), (B, Nx, Ny)):
+                raise ValueError("TimeStep: %s must be [Nx,Ny] or [B,Nx,Ny], got %s" % (n, tuple(t.shape)))
+        prob = _lib.make_problem(Nx, Ny, B, 1, 0, 0, float(dt), float(h),
+                                 device=dev.index if dev.index is not None else torch.cuda.current_device())
+        y = torch.empty_like(y132)
+        with torch.cuda.device(dev):
+            st = lib.wt_step_forward(ctypes.byref(prob), _lib.ptr(b32), int(b32.dim() == 3), _lib.ptr(c32),
+                                     int(c32.dim() == 3), _lib.ptr(y132), _lib.ptr(y232), _lib.ptr(y),
+                                     _lib.stream_ptr(dev))
+        _lib.check(st, "wt_step_forward")
+        _lib.count_launches(1)
+        ctx.prob = prob
+        ctx.save_for_backward(b32, c32, y132, y232)
+        ctx.dtypes = (b.dtype, c.dtype, y1.dtype, y2.dtype)
+        return y.to(y1.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        lib = _lib.load()
+        b32, c32, y1, y2 = ctx.saved_tensors
+        dev = y1.device
+        need = ctx.needs_input_grad
+        g = grad_output.detach().to(torch.float32).contiguous()
+        outs = [torch.empty_like(y1) if need[i] else None for i in range(4)]
+        with torch.cuda.device(dev):
+            st = lib.wt_step_backward(ctypes.byref(ctx.prob), _lib.ptr(b32), int(b32.dim() == 3), _lib.ptr(c32),
+                                      int(c32.dim() == 3), _lib.ptr(y1), _lib.ptr(y2), _lib.ptr(g),
+                                      _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]),
+                                      _lib.stream_ptr(dev))
+        _lib.check(st, "wt_step_backward")
+        _lib.count_launches(1)
+        gb, gc, gy1, gy2 = outs
+        # per-sample gradients are summed over the batch when the coefficient was shared (what autograd's
+        # sum_to_size does for the reference)
+        if gb is not None and b32.dim() == 2:
+            gb = gb.sum(0)
+        if gc is not None and c32.dim() == 2:
+            gc = gc.sum(0)
+        cast = lambda t, d: None if t is None else t.to(d)
+        bd, cd, y1d, y2d = ctx.dtypes
+        return cast(gb, bd), cast(gc, cd), cast(gy1, y1d), cast(gy2, y2d), None, None
+
+
+def time_step(b, c, y1, y2, dt, h):
+    return TimeStep.apply(b, c, y1, y2, dt, h)

@@ -1,0 +1,233 @@
+"""Geometry parameterisations: rho -> blur -> projection -> c(x,y), and the absorbing-layer profile b(x,y).
+
+API-compatible with wavetorch/geom.py (class names, constructor arguments, buffer/parameter names, properties
+`.c .b .rho .cmax .h .domain_shape`, `constrain_to_design_region()`, `state_reconstruction_args()`); evaluated
+once per forward in plain PyTorch on whatever device the module lives on, so autograd carries dLoss/dc from the
+CUDA adjoint back to `rho`.
+"""
+import math
+from copy import deepcopy
+from typing import Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .utils import to_tensor
+
+
+def disk_pixels(r, c, radius, shape=None):
+    """Integer pixels with ((rr-r)/radius)^2 + ((cc-c)/radius)^2 < 1 -- the old skimage.draw.circle the
+    reference calls at geom.py:149 and study/propagate.py:24 (removed from scikit-image >= 0.19)."""
+    radius = float(radius)
+    rr, cc = np.mgrid[int(math.floor(r - radius)):int(math.ceil(r + radius)) + 1,
+                      int(math.floor(c - radius)):int(math.ceil(c + radius)) + 1]
+    keep = ((rr - r) / radius) ** 2 + ((cc - c) / radius) ** 2 < 1.0
+    if shape is not None:
+        keep &= (rr >= 0) & (rr < shape[0]) & (cc >= 0) & (cc < shape[1])
+    return rr[keep], cc[keep]
+
+
+def _tanh_projection(rho, eta, beta):
+    """(tanh(beta*eta) + tanh(beta*(rho-eta))) / (tanh(beta*eta) + tanh(beta*(1-eta)))  (geom.py:217-222)."""
+    lo = torch.tanh(beta * eta)
+    return (lo + torch.tanh(beta * (rho - eta))) / (lo + torch.tanh(beta * (1.0 - eta)))
+
+
+class WaveGeometry(torch.nn.Module):
+    """Base class: holds the grid, the two material speeds and the PML damping profile (geom.py:11-85)."""
+
+    def __init__(self, domain_shape: Tuple, h: float, c0: float, c1: float, abs_N: int = 20, abs_sig: float = 11,
+                 abs_p: float = 4.0):
+        super().__init__()
+        assert len(domain_shape) == 2, \
+            "len(domain_shape) must be equal to 2: only two-dimensional (2D) domains are supported"
+        self.domain_shape = tuple(int(n) for n in domain_shape)
+        self.register_buffer("h", to_tensor(h))
+        self.register_buffer("c0", to_tensor(c0))
+        self.register_buffer("c1", to_tensor(c1))
+        self.register_buffer("abs_N", to_tensor(abs_N, dtype=torch.uint8))
+        self.register_buffer("abs_sig", to_tensor(abs_sig))
+        self.register_buffer("abs_p", to_tensor(abs_p, dtype=torch.uint8))
+        self._init_b(int(abs_N), float(abs_sig), float(abs_p))
+
+    def state_reconstruction_args(self):
+        return {"domain_shape": self.domain_shape, "h": self.h.item(), "c0": self.c0.item(), "c1": self.c1.item(),
+                "abs_N": self.abs_N.item(), "abs_sig": self.abs_sig.item(), "abs_p": self.abs_p.item()}
+
+    def __repr__(self):
+        return "WaveGeometry shape={}, h={}".format(self.domain_shape, self.h)
+
+    def forward(self):
+        raise NotImplementedError("WaveGeometry forward() is not implemented. It is a torch.nn.Module only so that "
+                                  "it can be a component of a WaveCell; its forward() should never be called.")
+
+    @property
+    def c(self):
+        raise NotImplementedError
+
+    @property
+    def b(self):
+        return self._b
+
+    @property
+    def cmax(self):
+        """Largest wave speed, for the CFL check."""
+        return max(self.c0.item(), self.c1.item())
+
+    def constrain_to_design_region(self):
+        pass
+
+    def _init_b(self, abs_N: int, abs_sig: float, abs_p: float):
+        """Polynomial absorber ramps on all four edges, combined as sqrt(bx^2 + by^2) (geom.py:63-85)."""
+        Nx, Ny = self.domain_shape
+        assert Nx > 2 * abs_N + 1, \
+            "The domain isn't large enough in the x-direction to fit absorbing layer. Nx = {} and N = {}".format(Nx, abs_N)
+        assert Ny > 2 * abs_N + 1, \
+            "The domain isn't large enough in the y-direction to fit absorbing layer. Ny = {} and N = {}".format(Ny, abs_N)
+        bx = torch.zeros(Nx, Ny)
+        by = torch.zeros(Nx, Ny)
+        if abs_N > 0:
+            ramp = abs_sig * torch.linspace(0.0, 1.0, abs_N + 1) ** abs_p
+            bx[:abs_N + 1, :] = ramp.flip(0)[:, None]
+            bx[Nx - abs_N - 1:, :] = ramp[:, None]
+            by[:, :abs_N + 1] = ramp.flip(0)[None, :]
+            by[:, Ny - abs_N - 1:] = ramp[None, :]
+        self.register_buffer("_b", torch.sqrt(bx ** 2 + by ** 2))
+
+
+class WaveGeometryHoley(WaveGeometry):
+    """Sum of exponentially decaying holes exp(-|r - r_i| / R_i), then projected (geom.py:88-132)."""
+
+    def __init__(self, domain_shape: Tuple, h: float, c0: float, c1: float, abs_N: int = 20, abs_sig: float = 11,
+                 abs_p: float = 4.0, eta: float = 0.5, beta: float = 100.0, x=None, y=None, r=None):
+        super().__init__(domain_shape, h, c0, c1, abs_N, abs_sig, abs_p)
+        self.x = torch.nn.Parameter(to_tensor(x))
+        self.y = torch.nn.Parameter(to_tensor(y))
+        self.r = torch.nn.Parameter(to_tensor(r))
+        self.register_buffer("eta", to_tensor(eta))
+        self.register_buffer("beta", to_tensor(beta))
+
+    def state_reconstruction_args(self):
+        mine = {"eta": self.eta.item(), "beta": self.beta.item(), "x": deepcopy(self.x.detach()),
+                "y": deepcopy(self.y.detach()), "r": deepcopy(self.r.detach())}
+        return {**super().state_reconstruction_args(), **mine}
+
+    def _rho(self):
+        dev, dt = self.x.device, self.x.dtype
+        ii = torch.arange(self.domain_shape[0], device=dev, dtype=dt)[:, None]
+        jj = torch.arange(self.domain_shape[1], device=dev, dtype=dt)[None, :]
+        rho = torch.zeros(self.domain_shape, device=dev, dtype=dt)
+        for ri, xi, yi in zip(self.r, self.x, self.y):
+            rho = rho + torch.exp(-torch.sqrt((ii - xi) ** 2 + (jj - yi) ** 2) / ri)
+        return _tanh_projection(rho, self.eta, self.beta)
+
+    @property
+    def rho(self):
+        return self._rho()
+
+    @property
+    def c(self):
+        return self.c0 + (self.c1 - self.c0) * self._rho()
+
+
+class WaveGeometryFreeForm(WaveGeometry):
+    """Pixel-wise density `rho` (the trainable Parameter), blurred and projected into c (geom.py:136-233)."""
+
+    def __init__(self, domain_shape: Tuple, h: float, c0: float, c1: float, abs_N: int = 20, abs_sig: float = 11,
+                 abs_p: float = 4.0, eta: float = 0.5, beta: float = 100.0, design_region=None, rho='half',
+                 blur_radius: int = 1, blur_N: int = 1):
+        super().__init__(domain_shape, h, c0, c1, abs_N, abs_sig, abs_p)
+        self.register_buffer("eta", to_tensor(eta))
+        self.register_buffer("beta", to_tensor(beta))
+        self._init_design_region(design_region, self.domain_shape)
+        self._init_rho(rho, self.domain_shape)
+        n = 2 * int(blur_radius) + 1
+        rr, cc = disk_pixels(blur_radius, blur_radius, blur_radius + 1, shape=(n, n))
+        kernel = torch.zeros((n, n), dtype=torch.get_default_dtype())
+        kernel[rr, cc] = 1
+        kernel = kernel / kernel.sum()
+        self.register_buffer("blur_kernel", kernel[None, None])
+        self.register_buffer("blur_N", to_tensor(blur_N, dtype=torch.int))
+        # The reference registers this buffer from blur_N as well (geom.py:156); only the kernel shape is used.
+        self.register_buffer("blur_radius", to_tensor(blur_N, dtype=torch.int))
+        self._blur_passes = int(blur_N)
+        self.constrain_to_design_region()
+
+    def state_reconstruction_args(self):
+        mine = {"eta": self.eta.item(), "beta": self.beta.item(), "design_region": deepcopy(self.design_region),
+                "rho": deepcopy(self.rho.detach()), "blur_radius": self.blur_radius.item(),
+                "blur_N": self.blur_N.item()}
+        return {**super().state_reconstruction_args(), **mine}
+
+    def __repr__(self):
+        return super().__repr__() + ", " + str(self.design_region.sum().item()) + " DOFs"
+
+    def _init_design_region(self, design_region, domain_shape):
+        if design_region is None:
+            design_region = torch.ones(domain_shape, dtype=torch.uint8)      # whole domain is designable
+        else:
+            assert tuple(design_region.shape) == tuple(domain_shape), \
+                "The design region shape must match domain shape; design_region.shape = {} domain_shape = {}".format(
+                    design_region.shape, domain_shape)
+            if isinstance(design_region, np.ndarray):
+                design_region = torch.from_numpy(design_region.astype(np.uint8))
+        self.register_buffer("design_region", design_region)
+
+    def _init_rho(self, rho, domain_shape):
+        if isinstance(rho, (torch.Tensor, np.ndarray)):
+            assert tuple(rho.shape) == tuple(domain_shape)
+            self.rho = torch.nn.Parameter(to_tensor(rho))
+        elif isinstance(rho, str):
+            if rho == 'rand':
+                self.rho = torch.nn.Parameter(torch.round(torch.rand(domain_shape)))
+            elif rho == 'half':
+                self.rho = torch.nn.Parameter(torch.full(domain_shape, 0.5))
+            elif rho == 'blank':
+                self.rho = torch.nn.Parameter(torch.zeros(domain_shape))
+            else:
+                raise ValueError('The domain initialization defined by `rho = %s` is invalid' % rho)
+        else:
+            raise ValueError('The domain initialization is invalid')
+
+    def constrain_to_design_region(self):
+        """Zero rho outside the design region and inside the absorber (geom.py:201-205)."""
+        with torch.no_grad():
+            self.rho[self.design_region == 0] = 0.0
+            self.rho[self.b > 0] = 0.0
+
+    def _apply_blur(self, rho):
+        """blur_N passes of the zero-padded disk stencil (geom.py:207-215).
+
+        Written as explicit shifted adds instead of F.conv2d: on CUDA, cuDNN convolutions (and their backward,
+        which carries dLoss/dc to rho) may run in TF32, which costs 3e-4 of relative accuracy on rho.grad --
+        measured on BASELINE config 2 -- while the parity bar is 1e-4.
+        """
+        kernel = self.blur_kernel[0, 0].to(rho.dtype)
+        n = kernel.shape[-1]
+        pad = n // 2
+        passes = getattr(self, "_blur_passes", None)
+        if passes is None:     # module rebuilt from a state_dict without going through __init__
+            passes = int(self.blur_N.item())
+        if getattr(self, "_blur_taps", None) is None or self._blur_taps[0] != n:
+            host = kernel.detach().cpu()
+            self._blur_taps = (n, [(i, j) for i in range(n) for j in range(n) if host[i, j] != 0])
+        Nx, Ny = rho.shape
+        for _ in range(passes):
+            padded = F.pad(rho, (pad, pad, pad, pad))
+            acc = None
+            for (i, j) in self._blur_taps[1]:
+                term = kernel[i, j] * padded[i:i + Nx, j:j + Ny]
+                acc = term if acc is None else acc + term
+            rho = acc
+        return rho
+
+    def _apply_projection(self, rho):
+        return _tanh_projection(rho, self.eta, self.beta)
+
+    def _rho_model(self):
+        return self._apply_projection(self._apply_blur(self.rho))
+
+    @property
+    def c(self):
+        return self.c0 + (self.c1 - self.c0) * self._rho_model()
