@@ -16,6 +16,9 @@
 // source.py:15-22, probe.py:14-27.
 #include <cooperative_groups.h>
 
+#include <mutex>
+#include <vector>
+
 #include "wt_common.cuh"
 #include "wt_resident.h"
 #include "wt_stream.h"
@@ -85,9 +88,110 @@ __device__ __forceinline__ void st_stream(float4* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- cluster ghost-row exchange -------------------------------------------------------------------
+// Ghost rows travel with st.async: a 16-byte store into the neighbour CTA's shared memory that also counts
+// its bytes on an mbarrier there (complete_tx).  The receiver waits on its own mbarrier only, so the time loop
+// contains no cluster-wide barrier and no cluster-scope fence (which would also wait for the tape stores).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float x, float y, float z, float w, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(
+                   remote_addr),
+               "r"(__float_as_uint(x)), "r"(__float_as_uint(y)), "r"(__float_as_uint(z)), "r"(__float_as_uint(w)),
+               "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WT_WAITC:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WT_DONEC;\n"
+      "bra WT_WAITC;\n"
+      "WT_DONEC:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Per-thread view of the decomposition and of the ghost exchange.
 template <int R>
-struct Patch {
-  float v[R][4];
+struct Lane {
+  int rank, cid, tid, run, j0, lr0, gi0, slab;
+  bool active;
+  bool edge_up, edge_dn;     // my patch borders the slab of rank-1 / rank+1
+  bool arm_up, arm_dn;       // I re-arm the corresponding mbarrier
+  uint32_t push_up, push_dn; // cluster address of the neighbour's ghost row slot (buffer 0)
+  uint32_t rbar_up, rbar_dn; // cluster address of the neighbour's mbarrier my push signals
+  uint64_t* gbar;            // [4] my mbarriers: {from above, from below} x {even, odd publish}.  Two per direction:
+                             // with one, a neighbour that runs ahead could complete the NEXT phase before a slow
+                             // thread of mine has tested the current one, and that thread would wait forever.
+  unsigned row_bytes;
+  unsigned npub;             // publishes so far (phase bookkeeping)
+
+  __device__ __forceinline__ void init(const ResArgs& a, float* fld, uint64_t* bars) {
+    cg::cluster_group cluster = cg::this_cluster();
+    rank = (a.C > 1) ? (int)cluster.block_rank() : 0;
+    cid = blockIdx.x / a.C;
+    tid = threadIdx.x;
+    active = tid < a.nact;
+    run = tid / a.P4;
+    j0 = 4 * (tid - run * a.P4);
+    lr0 = run * R;
+    gi0 = rank * a.Hc + lr0;
+    slab = (a.Hc + 2) * a.pitch;
+    gbar = bars;
+    row_bytes = (unsigned)a.P4 * 16u;
+    npub = 0;
+    edge_up = active && a.C > 1 && run == 0 && rank > 0;
+    edge_dn = active && a.C > 1 && run == a.runs - 1 && rank < a.C - 1;
+    arm_up = edge_up && j0 == 0;
+    arm_dn = edge_dn && j0 == 0;
+    push_up = push_dn = rbar_up = rbar_dn = 0;
+    if (edge_up) {   // my top row is the ghost row BELOW the last row of rank-1
+      push_up = mapa_u32(smem_u32(fld + (a.Hc + 1) * a.pitch + 4 + j0), rank - 1);
+      rbar_up = mapa_u32(smem_u32(bars + 2), rank - 1);
+    }
+    if (edge_dn) {   // my bottom row is the ghost row ABOVE the first row of rank+1
+      push_dn = mapa_u32(smem_u32(fld + 4 + j0), rank + 1);
+      rbar_dn = mapa_u32(smem_u32(bars + 0), rank + 1);
+    }
+    if (tid == 0) {
+      for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (a.C > 1 && rank > 0) { mbar_expect_tx(bars + 0, row_bytes); mbar_expect_tx(bars + 1, row_bytes); }
+      if (a.C > 1 && rank < a.C - 1) { mbar_expect_tx(bars + 2, row_bytes); mbar_expect_tx(bars + 3, row_bytes); }
+    }
+  }
+
+  // Write my R rows into slab buffer `which` (0/1) and push the rim rows to the neighbours.
+  __device__ __forceinline__ void publish(const ResArgs& a, float* fld, int which, const float (&v)[R][4]) {
+    float* buf = fld + which * slab;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      *reinterpret_cast<float4*>(buf + (lr0 + r + 1) * a.pitch + 4 + j0) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+    const uint32_t boff = (uint32_t)(which * slab) * 4u;
+    const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
+    if (edge_up) st_async_v4(push_up + boff, v[0][0], v[0][1], v[0][2], v[0][3], rbar_up + bsel);
+    if (edge_dn) st_async_v4(push_dn + boff, v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3], rbar_dn + bsel);
+  }
+
+  // Wait until the neighbours' rows of the latest publish have landed in my ghost rows; re-arm for the next one.
+  __device__ __forceinline__ void acquire_ghosts() {
+    const unsigned k = npub - 1u, sel = k & 1u, parity = (k >> 1) & 1u;
+    if (edge_up) {
+      mbar_wait_cluster(gbar + sel, parity);
+      if (arm_up) mbar_expect_tx(gbar + sel, row_bytes);        // re-arm for publish k+2
+    }
+    if (edge_dn) {
+      mbar_wait_cluster(gbar + 2 + sel, parity);
+      if (arm_dn) mbar_expect_tx(gbar + 2 + sel, row_bytes);
+    }
+  }
 };
 
 // Which of my 4R cells are sources?  m1: listed at least once, m2: listed at least twice (rnn.py:56-57 adds x
@@ -125,37 +229,17 @@ __device__ __forceinline__ void load_coef(const ResArgs& a, bool active, int gi0
     }
 }
 
-// Write my R rows into `buf` and, if they border another CTA's slab, into that CTA's ghost row.
-template <int R>
-__device__ __forceinline__ void publish(cg::cluster_group& cluster, const ResArgs& a, float* buf, int rank, int run,
-                                        int lr0, int j0, const float (&v)[R][4]) {
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-    *reinterpret_cast<float4*>(buf + (lr0 + r + 1) * a.pitch + 4 + j0) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-  if (a.C > 1) {
-    if (run == 0 && rank > 0) {
-      float* dst = cluster.map_shared_rank(buf + (a.Hc + 1) * a.pitch + 4 + j0, rank - 1);
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
-    }
-    if (run == a.runs - 1 && rank < a.C - 1) {
-      float* dst = cluster.map_shared_rank(buf + 4 + j0, rank + 1);
-      *reinterpret_cast<float4*>(dst) = make_float4(v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3]);
-    }
-  }
-}
-
 // Unscaled 5-point Laplacian of my patch; own cells come from registers, the rim from shared memory.
 template <int R>
-__device__ __forceinline__ void patch_laplacian(const ResArgs& a, const float* buf, int lr0, int j0,
-                                                const float (&v)[R][4], float (&lap)[R][4]) {
-  const float4 up = *reinterpret_cast<const float4*>(buf + lr0 * a.pitch + 4 + j0);
-  const float4 dn = *reinterpret_cast<const float4*>(buf + (lr0 + R + 1) * a.pitch + 4 + j0);
+__device__ __forceinline__ void patch_laplacian(int pitch, const float* own, const float (&v)[R][4], float (&lap)[R][4]) {
+  // `own` points at my first row inside the slab buffer
+  const float4 up = *reinterpret_cast<const float4*>(own - pitch);
+  const float4 dn = *reinterpret_cast<const float4*>(own + R * pitch);
   const float upv[4] = {up.x, up.y, up.z, up.w};
   const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const float* row = buf + (lr0 + r + 1) * a.pitch + 4 + j0;
-    const float lf = row[-1], rt = row[4];
+    const float lf = own[r * pitch - 1], rt = own[r * pitch + 4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float n = (r == 0) ? upv[k] : v[r - 1][k];
@@ -169,7 +253,7 @@ __device__ __forceinline__ void patch_laplacian(const ResArgs& a, const float* b
 
 template <int R>
 constexpr int res_max_threads() {
-  return R <= 2 ? 1024 : R == 3 ? 768 : R <= 5 ? 512 : R == 6 ? 384 : 256;
+  return R <= 1 ? 1024 : R == 2 ? 768 : R == 3 ? 640 : R == 4 ? 512 : R == 5 ? 384 : R == 6 ? 320 : 256;
 }
 
 // =================================================================================================
@@ -177,59 +261,57 @@ constexpr int res_max_threads() {
 // =================================================================================================
 template <int R>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (a.C > 1) ? (int)cluster.block_rank() : 0;
-  const int cid = blockIdx.x / a.C;
-  const int tid = threadIdx.x;
-  const bool active = tid < a.nact;
-  const int run = tid / a.P4;
-  const int j0 = 4 * (tid - run * a.P4);
-  const int lr0 = run * R;
-  const int gi0 = rank * a.Hc + lr0;
-  const int slab = (a.Hc + 2) * a.pitch;
-
   extern __shared__ float4 smem4[];
+  const int slab_f = (a.Hc + 2) * a.pitch;
   float* fld = reinterpret_cast<float*>(smem4);       // [2][slab]
-  float* xs = fld + 2 * slab;                          // [2][TB]
+  float* xs = fld + 2 * slab_f;                        // [2][TB]
   float* ps = xs + 2 * TB;                             // [2][TB][n_prb]
   int* poff = reinterpret_cast<int*>(ps + 2 * TB * a.n_prb);  // [n_prb] offset into a slab buffer, or -1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(poff + a.n_prb + (a.n_prb & 1));
 
+  Lane<R> L;
+  L.init(a, fld, bars);
+  const int tid = L.tid, NT = blockDim.x;
   float k1[R][4], k3[R][4];
-  load_coef<R>(a, active, gi0, j0, k1, k3);
+  load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
   unsigned m1, m2;
-  source_masks<R>(a, active, gi0, j0, m1, m2);
-  for (int p = tid; p < a.n_prb; p += blockDim.x) {
-    int li = a.prb_ij[2 * p] - rank * a.Hc, pj = a.prb_ij[2 * p + 1];
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
+  for (int p = tid; p < a.n_prb; p += NT) {
+    int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * a.pitch + 4 + pj : -1;
   }
-  for (int i = tid; i < 2 * slab; i += blockDim.x) fld[i] = 0.f;
-  auto sync = [&]() {
-    if (a.C > 1) cluster.sync(); else __syncthreads();
-  };
-  sync();
+  for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
+  if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
+  const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
+  const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;     // my first row inside a slab buffer
+  const size_t tape_step = (size_t)a.C * R * NT;        // float4 per time step of one sample
+  const size_t plane = (size_t)a.Nx * a.Ny;
 
-  for (int b = cid; b < a.B; b += a.n_clusters) {
+  for (int b = L.cid; b < a.B; b += a.n_clusters) {
     float v[R][4], w[R][4];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        int gi = gi0 + r, j = j0 + k;
-        bool ok = active && gi < a.Nx && j < a.Ny && !(a.flags & WT_F_ZERO_INIT);
+        int gi = L.gi0 + r, j = L.j0 + k;
+        bool ok = L.active && gi < a.Nx && j < a.Ny && !(a.flags & WT_F_ZERO_INIT);
         size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
         v[r][k] = ok ? a.u1[o] : 0.f;
         w[r][k] = ok ? a.u2[o] : 0.f;
       }
-    if (active) publish<R>(cluster, a, fld, rank, run, lr0, j0, v);
+    if (L.active) L.publish(a, fld, 0, v);
+    ++L.npub;
     const float* xb = a.x + (size_t)b * a.T;
-    for (int i = tid; i < TB && i < a.T; i += blockDim.x) xs[i] = xb[i];
-    sync();
+    for (int i = tid; i < TB && i < a.T; i += NT) xs[i] = xb[i];
+    __syncthreads();
 
-    int flushed = 0;
+    float4* tape = a.tape ? a.tape + (((size_t)b * a.T) * a.C + L.rank) * R * NT + tid : nullptr;
+    float* fout = a.fields ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
+
     auto flush = [&](int blk) {   // probe samples of time block blk -> HBM
       const int t0 = blk * TB, n = min(TB, a.T - t0);
       const float* src = ps + (blk & 1) * TB * a.n_prb;
-      for (int i = tid; i < n * a.n_prb; i += blockDim.x) {
+      for (int i = tid; i < n * a.n_prb; i += NT) {
         int p = i % a.n_prb;
         if (poff[p] >= 0) {
           float val = src[i];
@@ -239,86 +321,96 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
         }
       }
     };
-    auto record = [&](const float* buf, int t) {   // sample the probes of step t from the slab buffer holding u_t
-      if (tid < a.n_prb && poff[tid] >= 0) ps[((t / TB) & 1) * TB * a.n_prb + (t % TB) * a.n_prb + tid] = buf[poff[tid]];
-    };
-
-    for (int t = 0; t < a.T; ++t) {
-      const float* cur = fld + (t & 1) * slab;
-      float* nxt = fld + ((t + 1) & 1) * slab;
-      const int blk = t / TB, tt = t - blk * TB;
-      if (tt == 0 && (blk + 1) * TB < a.T) {   // stage the next block of x
-        float* dst = xs + ((blk + 1) & 1) * TB;
-        const int t1 = (blk + 1) * TB;
-        for (int i = tid; i < TB && t1 + i < a.T; i += blockDim.x) dst[i] = xb[t1 + i];
-      }
-      if (t > 0) {
-        record(cur, t - 1);
-        if (t - 1 >= (flushed + 1) * TB) { flush(flushed); ++flushed; }
-      }
-      if (active) {
+    // One time step: `cu` = u_t (kept), `pr` = u_{t-1} on entry and u_{t+1} on exit.  t is the index of the new field.
+    auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int t, int blk, int tt) {
+      const float* cur = fld + (t & 1) * L.slab;
+      L.acquire_ghosts();
+      if (t > 0 && my_poff >= 0) ps[(((t - 1) / TB) & 1) * TB * a.n_prb + ((t - 1) % TB) * a.n_prb + tid] = cur[my_poff];
+      if (L.active) {
         float lap[R][4];
-        patch_laplacian<R>(a, cur, lr0, j0, v, lap);
+        patch_laplacian<R>(a.pitch, cur + own, cu, lap);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float y = wt_update(k1[r][k], k3[r][k], v[r][k], w[r][k], lap[r][k]);
-            w[r][k] = v[r][k];
-            v[r][k] = y;
-          }
+          for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         if (m1) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t]
           const float xv = xs[(blk & 1) * TB + tt];
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (m1 >> (r * 4 + k) & 1u) v[r][k] += xv;
-              if (m2 >> (r * 4 + k) & 1u) v[r][k] += xv;
+              if (m1 >> (r * 4 + k) & 1u) pr[r][k] += xv;
+              if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
             }
         }
-        publish<R>(cluster, a, nxt, rank, run, lr0, j0, v);
-        if (a.tape) {
-          float4* tp = a.tape + ((((size_t)b * a.T + t) * a.C + rank) * R) * blockDim.x + tid;
+        L.publish(a, fld, (t + 1) & 1, pr);
+        if (tape) {
 #pragma unroll
-          for (int r = 0; r < R; ++r) st_stream(tp + (size_t)r * blockDim.x, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
+          for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
+          tape += tape_step;
         }
-        if (a.fields) {
+        if (fout) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            int gi = gi0 + r;
-            if (gi < a.Nx) {
-              float* f = a.fields + (((size_t)b * a.T + t) * a.Nx + gi) * a.Ny + j0;
+            if (L.gi0 + r < a.Nx) {
+              float* f = fout + (size_t)r * a.Ny;
               if (a.vec_fields) {
-                *reinterpret_cast<float4*>(f) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+                *reinterpret_cast<float4*>(f) = make_float4(pr[r][0], pr[r][1], pr[r][2], pr[r][3]);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  if (j0 + k < a.Ny) f[k] = v[r][k];
+                  if (L.j0 + k < a.Ny) f[k] = pr[r][k];
               }
             }
           }
+          fout += plane;
         }
       }
-      sync();
+      ++L.npub;
+      __syncthreads();
+    };
+
+    const int nblk = (a.T + TB - 1) / TB;
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int t0 = blk * TB, n = min(TB, a.T - t0);
+      if ((blk + 1) * TB < a.T) {   // stage the next block of x
+        float* dst = xs + ((blk + 1) & 1) * TB;
+        const int t1 = (blk + 1) * TB;
+        for (int i = tid; i < TB && t1 + i < a.T; i += NT) dst[i] = xb[t1 + i];
+      }
+      if (blk >= 2) flush(blk - 2);
+      int tt = 0;
+      for (; tt + 1 < n; tt += 2) {     // two steps per iteration: the two time levels swap roles, no moves
+        step(v, w, t0 + tt, blk, tt);
+        step(w, v, t0 + tt + 1, blk, tt + 1);
+      }
+      if (tt < n) {                      // odd tail (last block only): keep "v = latest" by swapping once
+        step(v, w, t0 + tt, blk, tt);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { float tmp = v[r][k]; v[r][k] = w[r][k]; w[r][k] = tmp; }
+      }
     }
-    record(fld + (a.T & 1) * slab, a.T - 1);
+    L.acquire_ghosts();   // consume the last publish so that no st.async is in flight past this point
+    if (my_poff >= 0) ps[(((a.T - 1) / TB) & 1) * TB * a.n_prb + ((a.T - 1) % TB) * a.n_prb + tid] = fld[(a.T & 1) * L.slab + my_poff];
     __syncthreads();
-    while (flushed * TB < a.T) { flush(flushed); ++flushed; }
+    for (int blk = max(0, nblk - 2); blk < nblk; ++blk) flush(blk);
     // final state back to HBM: u1 = latest field, u2 = the one before (cell.py:107)
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        int gi = gi0 + r, j = j0 + k;
-        if (active && gi < a.Nx && j < a.Ny) {
+        int gi = L.gi0 + r, j = L.j0 + k;
+        if (L.active && gi < a.Nx && j < a.Ny) {
           size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
           a.u1[o] = v[r][k];
           a.u2[o] = w[r][k];
         }
       }
-    sync();   // nobody may publish the next sample's initial field while a neighbour still reads this one
+    __syncthreads();
   }
+  if (a.C > 1) cg::this_cluster().sync();   // nobody exits while a neighbour could still address its shared memory
 }
 
 // =================================================================================================
@@ -326,50 +418,43 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 // =================================================================================================
 template <int R>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (a.C > 1) ? (int)cluster.block_rank() : 0;
-  const int cid = blockIdx.x / a.C;
-  const int tid = threadIdx.x;
-  const bool active = tid < a.nact;
-  const int run = tid / a.P4;
-  const int j0 = 4 * (tid - run * a.P4);
-  const int lr0 = run * R;
-  const int gi0 = rank * a.Hc + lr0;
-  const int slab = (a.Hc + 2) * a.pitch;
   const int NT = blockDim.x;
+  const int slab_f = (a.Hc + 2) * a.pitch;
   const unsigned stage_bytes = (unsigned)(R * NT * sizeof(float4));
 
   extern __shared__ float4 smem4[];
   float4* ring = smem4;                                        // [RING][R*NT]
   float* fld = reinterpret_cast<float*>(ring + RING * R * NT);  // [2][slab]   P = a3*lambda
-  float* ss = fld + 2 * slab;                                   // [2][TB][n_prb] probe seeds
+  float* ss = fld + 2 * slab_f;                                 // [2][TB][n_prb] probe seeds
   float* gxs = ss + 2 * TB * a.n_prb;                           // [2][TB]     dLoss/dx staging
   int* pown = reinterpret_cast<int*>(gxs + 2 * TB);             // [n_prb] owning thread, or -1
   int* pcell = pown + a.n_prb;                                  // [n_prb] cell index inside the owner's patch
-  uint64_t* full = reinterpret_cast<uint64_t*>(pcell + a.n_prb + ((2 * a.n_prb) & 1));  // [RING], 8-byte aligned
+  uint64_t* full = reinterpret_cast<uint64_t*>(pcell + a.n_prb);  // [RING] tape stages; 8-byte aligned (even word count)
+  uint64_t* bars = full + RING;                                 // [4] ghost rows
 
+  Lane<R> L;
+  L.init(a, fld, bars);
+  const int tid = L.tid;
   float k1[R][4], k3[R][4];
-  load_coef<R>(a, active, gi0, j0, k1, k3);
+  load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
   unsigned m1, m2;
-  source_masks<R>(a, active, gi0, j0, m1, m2);
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
-    int li = a.prb_ij[2 * p] - rank * a.Hc, pj = a.prb_ij[2 * p + 1];
+    int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     bool mine = li >= 0 && li < a.Hc;
     pown[p] = mine ? (li / R) * a.P4 + pj / 4 : -1;
     pcell[p] = mine ? (li % R) * 4 + (pj & 3) : 0;
   }
-  for (int i = tid; i < 2 * slab; i += NT) fld[i] = 0.f;
+  for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   for (int i = tid; i < 2 * TB; i += NT) gxs[i] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < RING; ++s) mbar_init(full + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  auto sync = [&]() {
-    if (a.C > 1) cluster.sync(); else __syncthreads();
-  };
-  sync();
+  if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
   bool has_probe = false;
   for (int p = 0; p < a.n_prb; ++p) has_probe |= (pown[p] == tid);
+  const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
 
   float G[R][4];
 #pragma unroll
@@ -378,14 +463,14 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     for (int k = 0; k < 4; ++k) G[r][k] = 0.f;
 
   unsigned it_global = 0;   // tape stages consumed so far (ring slot / parity bookkeeping across samples)
-  for (int b = cid; b < a.B; b += a.n_clusters) {
+  for (int b = L.cid; b < a.B; b += a.n_clusters) {
     float lam[R][4], c2[R][4];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k) { lam[r][k] = 0.f; c2[r][k] = 0.f; }
 
-    auto tape_ptr = [&](int t) { return a.tape + ((((size_t)b * a.T + t) * a.C + rank) * R) * NT; };
+    auto tape_ptr = [&](int t) { return a.tape + ((((size_t)b * a.T + t) * a.C + L.rank) * R) * NT; };
     auto stage_seeds = [&](int blk) {   // seeds of time block blk: dLoss/d(raw probe value)
       const int t0 = blk * TB, n = min(TB, a.T - t0);
       float* dst = ss + (blk & 1) * TB * a.n_prb;
@@ -414,16 +499,16 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       }
     }
     stage_seeds((a.T - 1) / TB);
-    sync();
+    __syncthreads();
 
     for (int t = a.T - 1, it = 0; t >= 0; --t, ++it) {
       const int blk = t / TB, tt = t - blk * TB;
-      float* cur = fld + (it & 1) * slab;
+      float* cur = fld + (it & 1) * L.slab;
       if ((t == a.T - 1 || tt == TB - 1) && blk > 0) stage_seeds(blk - 1);
       if (a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
       const unsigned slot = (it_global + it) % RING, parity = ((it_global + it) / RING) & 1u;
       float pv[R][4];
-      if (active) {
+      if (L.active) {
         if (has_probe) {   // lambda_t += dLoss/du_t through the probes
           for (int p = 0; p < a.n_prb; ++p)
             if (pown[p] == tid) {
@@ -458,12 +543,18 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
             pv[r][k] = k3[r][k] * lam[r][k];
           }
         }
-        publish<R>(cluster, a, cur, rank, run, lr0, j0, pv);
+        L.publish(a, fld, it & 1, pv);
       }
-      sync();
-      if (active) {
+      ++L.npub;
+      __syncthreads();
+      if (tid == 0 && it + RING < a.T) {   // every thread has read this slot: refill it RING steps ahead
+        mbar_expect_tx(full + slot, stage_bytes);
+        bulk_g2s(ring + slot * R * NT, tape_ptr(t - RING), stage_bytes, full + slot);
+      }
+      L.acquire_ghosts();
+      if (L.active) {
         float lapP[R][4];
-        patch_laplacian<R>(a, cur, lr0, j0, pv, lapP);
+        patch_laplacian<R>(a.pitch, cur + own, pv, lapP);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -473,24 +564,21 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
             lam[r][k] = nl;
           }
       }
-      if (tid == 0 && it + RING < a.T) {   // every thread passed the barrier after reading this slot: refill it
-        mbar_expect_tx(full + slot, stage_bytes);
-        bulk_g2s(ring + slot * R * NT, tape_ptr(t - RING), stage_bytes, full + slot);
-      }
     }
     it_global += (unsigned)a.T;
-    sync();
-    if (a.grad_x) { flush_gx(0); }
-    sync();
+    __syncthreads();
+    if (a.grad_x) flush_gx(0);
+    __syncthreads();
   }
   // per-cluster partial of sum_{b,t} L(u_{t-1})*lambda_t ; reduced and scaled by k_finish_grad
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      int gi = gi0 + r, j = j0 + k;
-      if (active && gi < a.Nx && j < a.Ny) a.Gpart[((size_t)cid * a.Nx + gi) * a.Ny + j] = G[r][k];
+      int gi = L.gi0 + r, j = L.j0 + k;
+      if (L.active && gi < a.Nx && j < a.Ny) a.Gpart[((size_t)L.cid * a.Nx + gi) * a.Ny + j] = G[r][k];
     }
+  if (a.C > 1) cg::this_cluster().sync();
 }
 
 // =================================================================================================
@@ -499,22 +587,64 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 static size_t smem_fwd_bytes(int Hc, int pitch, int n_prb) {
-  return (size_t)2 * (Hc + 2) * pitch * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)n_prb * 4 + 16;
+  return (size_t)2 * (Hc + 2) * pitch * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)(n_prb + 1) * 4 + 4 * 8 + 16;
 }
 static size_t smem_adj_bytes(int Hc, int pitch, int n_prb, int R, int threads) {
   return (size_t)RING * R * threads * 16 + (size_t)2 * (Hc + 2) * pitch * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
-         (size_t)2 * n_prb * 4 + 8 + RING * 8 + 16;
+         (size_t)2 * n_prb * 4 + 8 + RING * 8 + 4 * 8 + 16;
 }
 
 static int max_threads_for(int R) {
   switch (R) {
-    case 1: case 2: return 1024;
-    case 3: return 768;
-    case 4: case 5: return 512;
-    case 6: return 384;
+    case 1: return 1024;
+    case 2: return 768;
+    case 3: return 640;
+    case 4: return 512;
+    case 5: return 384;
+    case 6: return 320;
     case 8: return 256;
     default: return 0;
   }
+}
+
+template <typename K>
+static int active_clusters(K kernel, int C, int threads, size_t smem) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  if (C > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C * 1024);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// Clusters that can be co-resident for both kernels of a decomposition (0 = cannot launch).  Cached per device.
+static int resident_clusters(int device, int R, int C, int threads, size_t smem_fwd, size_t smem_bwd) {
+  struct Key { int dev, R, C, threads; size_t sf, sb; int n; };
+  static std::mutex mu;
+  static std::vector<Key> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Key& k : cache)
+    if (k.dev == device && k.R == R && k.C == C && k.threads == threads && k.sf == smem_fwd && k.sb == smem_bwd) return k.n;
+  int nf = 0, nb = 0;
+  switch (R) {
+#define WT_OCC(R_) case R_: nf = active_clusters(k_res_fwd<R_>, C, threads, smem_fwd); nb = active_clusters(k_res_adj<R_>, C, threads, smem_bwd); break;
+    WT_OCC(1) WT_OCC(2) WT_OCC(3) WT_OCC(4) WT_OCC(5) WT_OCC(6) WT_OCC(8)
+#undef WT_OCC
+    default: break;
+  }
+  int n = nf < nb ? nf : nb;
+  cache.push_back(Key{device, R, C, threads, smem_fwd, smem_bwd, n});
+  return n;
 }
 
 bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_adjoint, wt_plan* plan) {
@@ -544,8 +674,9 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
       const double rim = (double)(4 * R) / (4 * R + 2 * R + 8);   // own cells / (own + rim loads)
       const double lane = (double)nact / threads;
       const double sync_cost = C > 1 ? 0.85 : 1.0;
-      const double par = threads >= 256 ? 1.0 : threads / 256.0;
-      const double score = busy * rim * lane * sync_cost * par;
+      const double par = threads >= 384 ? 1.0 : threads / 384.0;
+      const double regs = R >= 6 ? 0.8 : 1.0;   // measured: R = 4..5 beats 6..8 (register pressure in the adjoint)
+      const double score = busy * rim * lane * sync_cost * par * regs;
       if (score > best_score) { best_score = score; bestC = C; bestR = R; }
     }
   }
@@ -557,8 +688,9 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
   plan->rows_per_thread = bestR;
   plan->threads = threads;
   plan->rows_per_cta = Hc;
-  int ncl = prop.multiProcessorCount / bestC;
-  if (ncl < 1) ncl = 1;
+  int ncl = resident_clusters(p->device, bestR, bestC, threads, smem_fwd_bytes(Hc, pitch, p->n_prb),
+                              smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads));
+  if (ncl < 1) return false;
   plan->n_clusters = p->B < ncl ? p->B : ncl;
   plan->smem_fwd = (int)smem_fwd_bytes(Hc, pitch, p->n_prb);
   plan->smem_bwd = (int)smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads);
