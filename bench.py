@@ -100,52 +100,58 @@ def run_reference(args):
 # clocks
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU through NVML every few milliseconds while the timed
+    regions run (the profiling recipe's nvidia-smi clocks line, taken in-process so that short regions get samples)."""
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4,
+               "hw_power_brake_slowdown": 0x80}
+
+    def __init__(self, index, period_s=0.004):
+        self.index, self.period, self.samples, self.stop_flag, self.thread = index, period_s, [], False, None
+        self.err = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.index])
+                except Exception:
+                    phys = self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                ut = pynvml.nvmlDeviceGetUtilizationRates(h).gpu
+                self.samples.append((sm, pw, rs, ut))
+                time.sleep(self.period)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [s.strip() for s in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: %s" % self.err]}
+        busy = [s for s in self.samples if s[3] > 0] or self.samples
+        bits = 0
+        for s in busy:
+            bits |= s[2]
+        reasons = sorted(n for n, b in self.REASONS.items() if bits & b)
+        return {"sm_mhz": statistics.median(s[0] for s in busy), "sm_max_mhz": float(self.max_sm),
+                "power_w_max": max(s[1] for s in busy), "samples": len(self.samples), "samples_under_load": len(busy),
+                "reasons": reasons, "how": "NVML polled every %d ms across all timed regions" % int(self.period * 1e3)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -223,8 +229,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, warm=0):
         """CUDA-event time of `steps` calls, max over ranks; returns ms per step."""
+        for _ in range(warm):
+            fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
         e0.record()
@@ -237,11 +245,11 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps
 
-    for _ in range(max(args.warmup, 3)):
-        train_step(x_dev, labels)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        train_step(x_dev, labels)
     l0 = _lib.launch_count
     t_wall = time.perf_counter()
     ms_step = timed(lambda: train_step(x_dev, labels), args.steps)
@@ -266,7 +274,6 @@ def run_ours(args):
     for _ in range(3):
         fwd_only()
     ms_fwd = timed(fwd_only, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
 
     # dominant kernels, timed alone with CUDA events on the launching stream
     out = model(x_dev)
@@ -276,7 +283,7 @@ def run_ours(args):
     def fwd_tape():
         return model(x_dev)
 
-    ms_fwd_tape = timed(fwd_tape, max(3, args.steps // 2))
+    ms_fwd_tape = timed(fwd_tape, max(3, args.steps // 2), warm=2)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     bw_ms = []
     for _ in range(max(3, args.steps // 2)):
@@ -289,6 +296,7 @@ def run_ours(args):
         bw_ms.append(ev[0].elapsed_time(ev[1]))
         model.zero_grad(set_to_none=True)
     ms_bwd = statistics.median(bw_ms)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:

@@ -252,7 +252,7 @@ def test_full_size_properties():
     assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g1.cpu().numpy()) < 2e-5
 
 
-@pytest.mark.parametrize("cluster,rows", [(2, 5), (2, 3), (2, 4), (4, 2), (4, 4), (4, 5), (8, 1), (8, 2), (8, 5), (16, 2)])
+@pytest.mark.parametrize("cluster,rows", [(2, 5), (2, 3), (2, 4), (4, 2), (4, 4), (4, 5), (8, 1), (8, 2), (8, 5)])
 def test_resident_decompositions_agree(cluster, rows):
     """Every (cluster size, rows per thread) decomposition of the on-chip path computes the same thing."""
     B, T = 5, 130

@@ -10,6 +10,8 @@ from test_gpu_parity import _vowel_model
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 combos = [(2, 8), (2, 6), (2, 5), (2, 4), (2, 3), (4, 8), (4, 5), (4, 4), (4, 3), (4, 2), (8, 5), (8, 4), (8, 2), (8, 1), (16, 2), (16, 1)]
+if os.environ.get("SWEEP"):
+    combos = [tuple(int(v) for v in c.split("x")) for c in os.environ["SWEEP"].split(",")]
 m = _vowel_model()
 x = torch.tensor(wo.synthetic_vowels(B, T), device="cuda")
 labels = torch.arange(B, device="cuda") % 3
