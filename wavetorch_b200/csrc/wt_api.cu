@@ -55,8 +55,9 @@ static int make_plan(const wt_problem* p, bool need_adjoint, bool need_general, 
   bool force_res = (p->flags & WT_F_FORCE_RESIDENT) || (env && env[0] == 'r');
   if (!force_stream && !need_general && p->T >= 1 && resident_plan(p, prop, need_adjoint, plan)) return WT_OK;
   if (force_res) {
-    set_error("problem %dx%d B=%d cannot run on the resident path (nonlinear=%d, n_prb=%d)", p->Nx, p->Ny, p->B,
-              plan->nonlinear, p->n_prb);
+    int nlm = plan->nonlinear;
+    set_error("problem %dx%d B=%d cannot run on the resident path (nonlinear=%d, n_prb=%d)", p->Nx, p->Ny, p->B, nlm,
+              p->n_prb);
     return WT_EUNSUPPORTED;
   }
   plan->path = WT_PATH_STREAM;
@@ -110,7 +111,7 @@ int wt_forward(const wt_problem* p, const float* c, const float* b, const float*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (p->T == 0) return WT_OK;
   if (plan.path == WT_PATH_RESIDENT)
-    return resident_forward(p, plan, c, b, x, src_ij, prb_ij, prb_square, u1, u2, probe_out, probe_raw, fields_out,
+    return resident_forward(p, plan, c, b, rho, x, src_ij, prb_ij, prb_square, u1, u2, probe_out, probe_raw, fields_out,
                             history, workspace, st);
   return stream_forward(p, c, b, rho, x, src_ij, prb_ij, prb_square, u1, u2, probe_out, probe_raw, fields_out, history,
                         workspace, st);
@@ -151,7 +152,7 @@ int wt_backward(const wt_problem* p, const float* c, const float* b, const float
     return WT_OK;
   }
   if (plan.path == WT_PATH_RESIDENT)
-    return resident_backward(p, plan, c, b, src_ij, prb_ij, prb_square, grad_probe, probe_raw, history, grad_c, grad_b,
+    return resident_backward(p, plan, c, b, rho, src_ij, prb_ij, prb_square, grad_probe, probe_raw, history, grad_c, grad_b,
                              grad_rho, grad_x, workspace, st);
   return stream_backward(p, c, b, rho, src_ij, prb_ij, prb_square, grad_probe, probe_raw, grad_fields, history, adj1,
                          adj2, grad_c, grad_b, grad_rho, grad_x, workspace, st);

@@ -14,247 +14,14 @@
 //
 // Reference semantics: wavetorch/rnn.py:36-70, cell.py:12-17, cell.py:27-44, operators.py:5-11,
 // source.py:15-22, probe.py:14-27.
-#include <cooperative_groups.h>
-
 #include <mutex>
 #include <vector>
 
-#include "wt_common.cuh"
 #include "wt_resident.h"
+#include "wt_resident_dev.cuh"
 #include "wt_stream.h"
 
-namespace cg = cooperative_groups;
-
 namespace wt {
-
-constexpr int TB = 64;        // time steps per x / probe staging block
-constexpr int RING = 4;       // tape prefetch depth (adjoint)
-constexpr int MAX_PRB = 64;   // probes the resident path stages per CTA
-
-struct ResArgs {
-  int Nx, Ny, B, T;
-  int C, Hc, P4, pitch, nact, runs;
-  int n_src, n_prb, n_clusters;
-  unsigned flags;
-  int vec_fields;            // fields_out may be written with float4
-  const float* a1;
-  const float* a3;
-  const float* x;
-  const int32_t* src_ij;
-  const int32_t* prb_ij;
-  const int32_t* prb_sq;
-  float* u1;
-  float* u2;
-  float* probe_out;
-  float* probe_raw;
-  float* fields;
-  float4* tape;
-  // adjoint only
-  const float* grad_probe;
-  float* grad_x;
-  float* Gpart;              // [n_clusters, Nx, Ny]
-  int* status;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WT_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WT_DONE;\n"
-      "bra WT_WAIT;\n"
-      "WT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void st_stream(float4* p, float4 v) {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-// ---- cluster ghost-row exchange -------------------------------------------------------------------
-// Ghost rows travel with st.async: a 16-byte store into the neighbour CTA's shared memory that also counts
-// its bytes on an mbarrier there (complete_tx).  The receiver waits on its own mbarrier only, so the time loop
-// contains no cluster-wide barrier and no cluster-scope fence (which would also wait for the tape stores).
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float x, float y, float z, float w, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(
-                   remote_addr),
-               "r"(__float_as_uint(x)), "r"(__float_as_uint(y)), "r"(__float_as_uint(z)), "r"(__float_as_uint(w)),
-               "r"(remote_bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WT_WAITC:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WT_DONEC;\n"
-      "bra WT_WAITC;\n"
-      "WT_DONEC:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-// Per-thread view of the decomposition and of the ghost exchange.
-template <int R>
-struct Lane {
-  int rank, cid, tid, run, j0, lr0, gi0, slab;
-  bool active;
-  bool edge_up, edge_dn;     // my patch borders the slab of rank-1 / rank+1
-  bool arm_up, arm_dn;       // I re-arm the corresponding mbarrier
-  uint32_t push_up, push_dn; // cluster address of the neighbour's ghost row slot (buffer 0)
-  uint32_t rbar_up, rbar_dn; // cluster address of the neighbour's mbarrier my push signals
-  uint64_t* gbar;            // [4] my mbarriers: {from above, from below} x {even, odd publish}.  Two per direction:
-                             // with one, a neighbour that runs ahead could complete the NEXT phase before a slow
-                             // thread of mine has tested the current one, and that thread would wait forever.
-  unsigned row_bytes;
-  unsigned npub;             // publishes so far (phase bookkeeping)
-
-  __device__ __forceinline__ void init(const ResArgs& a, float* fld, uint64_t* bars) {
-    cg::cluster_group cluster = cg::this_cluster();
-    rank = (a.C > 1) ? (int)cluster.block_rank() : 0;
-    cid = blockIdx.x / a.C;
-    tid = threadIdx.x;
-    active = tid < a.nact;
-    run = tid / a.P4;
-    j0 = 4 * (tid - run * a.P4);
-    lr0 = run * R;
-    gi0 = rank * a.Hc + lr0;
-    slab = (a.Hc + 2) * a.pitch;
-    gbar = bars;
-    row_bytes = (unsigned)a.P4 * 16u;
-    npub = 0;
-    edge_up = active && a.C > 1 && run == 0 && rank > 0;
-    edge_dn = active && a.C > 1 && run == a.runs - 1 && rank < a.C - 1;
-    arm_up = edge_up && j0 == 0;
-    arm_dn = edge_dn && j0 == 0;
-    push_up = push_dn = rbar_up = rbar_dn = 0;
-    if (edge_up) {   // my top row is the ghost row BELOW the last row of rank-1
-      push_up = mapa_u32(smem_u32(fld + (a.Hc + 1) * a.pitch + 4 + j0), rank - 1);
-      rbar_up = mapa_u32(smem_u32(bars + 2), rank - 1);
-    }
-    if (edge_dn) {   // my bottom row is the ghost row ABOVE the first row of rank+1
-      push_dn = mapa_u32(smem_u32(fld + 4 + j0), rank + 1);
-      rbar_dn = mapa_u32(smem_u32(bars + 0), rank + 1);
-    }
-    if (tid == 0) {
-      for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      if (a.C > 1 && rank > 0) { mbar_expect_tx(bars + 0, row_bytes); mbar_expect_tx(bars + 1, row_bytes); }
-      if (a.C > 1 && rank < a.C - 1) { mbar_expect_tx(bars + 2, row_bytes); mbar_expect_tx(bars + 3, row_bytes); }
-    }
-  }
-
-  // Write my R rows into slab buffer `which` (0/1) and push the rim rows to the neighbours.
-  __device__ __forceinline__ void publish(const ResArgs& a, float* fld, int which, const float (&v)[R][4]) {
-    float* buf = fld + which * slab;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      *reinterpret_cast<float4*>(buf + (lr0 + r + 1) * a.pitch + 4 + j0) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-    const uint32_t boff = (uint32_t)(which * slab) * 4u;
-    const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
-    if (edge_up) st_async_v4(push_up + boff, v[0][0], v[0][1], v[0][2], v[0][3], rbar_up + bsel);
-    if (edge_dn) st_async_v4(push_dn + boff, v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3], rbar_dn + bsel);
-  }
-
-  // Wait until the neighbours' rows of the latest publish have landed in my ghost rows; re-arm for the next one.
-  __device__ __forceinline__ void acquire_ghosts() {
-    const unsigned k = npub - 1u, sel = k & 1u, parity = (k >> 1) & 1u;
-    if (edge_up) {
-      mbar_wait_cluster(gbar + sel, parity);
-      if (arm_up) mbar_expect_tx(gbar + sel, row_bytes);        // re-arm for publish k+2
-    }
-    if (edge_dn) {
-      mbar_wait_cluster(gbar + 2 + sel, parity);
-      if (arm_dn) mbar_expect_tx(gbar + 2 + sel, row_bytes);
-    }
-  }
-};
-
-// Which of my 4R cells are sources?  m1: listed at least once, m2: listed at least twice (rnn.py:56-57 adds x
-// once per listing).  Three or more listings of one pixel are not supported by this path (status flag).
-template <int R>
-__device__ __forceinline__ void source_masks(const ResArgs& a, bool active, int gi0, int j0, unsigned& m1,
-                                             unsigned& m2) {
-  m1 = 0; m2 = 0;
-  if (!active) return;
-  for (int s = 0; s < a.n_src; ++s) {
-    int si = a.src_ij[2 * s] - gi0, sj = a.src_ij[2 * s + 1] - j0;
-    if (si >= 0 && si < R && sj >= 0 && sj < 4) {
-      unsigned bit = 1u << (si * 4 + sj);
-      if (m1 & bit) {
-        if (m2 & bit) atomicExch(a.status, 1);
-        m2 |= bit;
-      } else {
-        m1 |= bit;
-      }
-    }
-  }
-}
-
-template <int R>
-__device__ __forceinline__ void load_coef(const ResArgs& a, bool active, int gi0, int j0, float (&k1)[R][4],
-                                          float (&k3)[R][4]) {
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int gi = gi0 + r, j = j0 + k;
-      bool ok = active && gi < a.Nx && j < a.Ny;
-      k1[r][k] = ok ? a.a1[(size_t)gi * a.Ny + j] : 0.f;
-      k3[r][k] = ok ? a.a3[(size_t)gi * a.Ny + j] : 0.f;
-    }
-}
-
-// Unscaled 5-point Laplacian of my patch; own cells come from registers, the rim from shared memory.
-template <int R>
-__device__ __forceinline__ void patch_laplacian(int pitch, const float* own, const float (&v)[R][4], float (&lap)[R][4]) {
-  // `own` points at my first row inside the slab buffer
-  const float4 up = *reinterpret_cast<const float4*>(own - pitch);
-  const float4 dn = *reinterpret_cast<const float4*>(own + R * pitch);
-  const float upv[4] = {up.x, up.y, up.z, up.w};
-  const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const float lf = own[r * pitch - 1], rt = own[r * pitch + 4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float n = (r == 0) ? upv[k] : v[r - 1][k];
-      float s = (r == R - 1) ? dnv[k] : v[r + 1][k];
-      float w = (k == 0) ? lf : v[r][k - 1];
-      float e = (k == 3) ? rt : v[r][k + 1];
-      lap[r][k] = fmaf(-4.f, v[r][k], (n + s) + (w + e));
-    }
-  }
-}
-
-template <int R>
-constexpr int res_max_threads() {
-  return R <= 1 ? 1024 : R == 2 ? 768 : R == 3 ? 640 : R == 4 ? 512 : R == 5 ? 384 : R == 6 ? 320 : 256;
-}
 
 // =================================================================================================
 // forward
@@ -647,36 +414,75 @@ static int resident_clusters(int device, int R, int C, int threads, size_t smem_
   return n;
 }
 
+static int res_nl_clusters_cached(int device, int R, int nl, int C, int threads, size_t sf, size_t sb) {
+  struct Key { int dev, R, nl, C, threads; size_t sf, sb; int n; };
+  static std::mutex mu;
+  static std::vector<Key> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Key& k : cache)
+    if (k.dev == device && k.R == R && k.nl == nl && k.C == C && k.threads == threads && k.sf == sf && k.sb == sb) return k.n;
+  int n = res_nl_clusters(R, nl, C, threads, sf, sb);
+  cache.push_back(Key{device, R, nl, C, threads, sf, sb, n});
+  return n;
+}
+
 bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_adjoint, wt_plan* plan) {
-  if (nonlinear_mask(p) || (p->flags & WT_F_NEED_GRAD_B)) return false;
+  const int nl = nonlinear_mask(p);
+  if (p->flags & WT_F_NEED_GRAD_B) return false;
+  if (nl && !(p->flags & WT_F_ZERO_INIT)) return false;   // the on-chip nonlinear adjoint assumes zero initial fields
   if (p->n_prb > MAX_PRB || p->T < 1) return false;
   const int P4 = (p->Ny + 3) / 4, pitch = 4 * P4 + 4;
   const int smem_cap = (int)prop.sharedMemPerBlockOptin;
-  static const int Rs[] = {8, 6, 5, 4, 3, 2, 1};
+  static const int Rs_lin[] = {8, 6, 5, 4, 3, 2, 1};
+  static const int Rs_nl[] = {4, 3, 2, 1};
   static const int Cs[] = {1, 2, 4, 8, 16};
+  const int* Rs = nl ? Rs_nl : Rs_lin;
+  const int nR = nl ? 4 : 7;
+  auto ring_for = [&](int Hc, int R, int threads) {   // deepest tape ring that fits (nonlinear stages are twice as big)
+    for (int ring = RING; ring >= 2; --ring)
+      if ((int)res_nl_smem_adj(Hc, pitch, p->n_prb, R, threads, ring) <= smem_cap) return ring;
+    return 0;
+  };
   int bestC = 0, bestR = 0;
   double best_score = -1;
   for (int C : Cs) {
     if (p->cluster && C != p->cluster) continue;
     if (C > 8 && !p->cluster) continue;   // non-portable cluster sizes only on request
-    for (int R : Rs) {
+    for (int ri = 0; ri < nR; ++ri) {
+      const int R = Rs[ri];
       if (p->rows_per_thread && R != p->rows_per_thread) continue;
       const int Hc = round_up((p->Nx + C - 1) / C, R);
       if ((C - 1) * Hc >= p->Nx) continue;            // every CTA must own at least one real row
       const int runs = Hc / R, nact = runs * P4, threads = round_up(nact, 32);
-      if (threads > max_threads_for(R)) continue;
-      size_t sm = need_adjoint ? smem_adj_bytes(Hc, pitch, p->n_prb, R, threads) : smem_fwd_bytes(Hc, pitch, p->n_prb);
-      if ((int)sm > smem_cap) continue;
-      // score: SMs kept busy x work per thread efficiency (bigger patches amortise the rim reads)
-      const double ctas = (double)p->B * C;
-      const double waves = ctas / prop.multiProcessorCount;
-      const double busy = waves <= 1.0 ? waves : waves / (double)((long)waves + (waves > (long)waves ? 1 : 0));
+      if (threads > (nl ? res_nl_max_threads_rt(R) : max_threads_for(R))) continue;
+      if (nl) {
+        if (!ring_for(Hc, R, threads)) continue;
+      } else {
+        size_t sm = need_adjoint ? smem_adj_bytes(Hc, pitch, p->n_prb, R, threads) : smem_fwd_bytes(Hc, pitch, p->n_prb);
+        if ((int)sm > smem_cap) continue;
+      }
+      // estimated time per step ~ (waves of clusters) x (rows per CTA) / (per-thread efficiency)
+      size_t sf, sb;
+      int ncl;
+      if (nl) {
+        sf = res_nl_smem_fwd(Hc, pitch, p->n_prb);
+        sb = res_nl_smem_adj(Hc, pitch, p->n_prb, R, threads, ring_for(Hc, R, threads));
+        ncl = res_nl_clusters_cached(p->device, R, nl, C, threads, sf, sb);
+      } else {
+        sf = smem_fwd_bytes(Hc, pitch, p->n_prb);
+        sb = smem_adj_bytes(Hc, pitch, p->n_prb, R, threads);
+        ncl = resident_clusters(p->device, R, C, threads, sf, sb);
+      }
+      if (ncl < 1) continue;
+      const int waves = (p->B + ncl - 1) / ncl;
+      const int used = p->B < ncl ? p->B : ncl;
+      const int per_sm = (used * C + prop.multiProcessorCount - 1) / prop.multiProcessorCount;   // CTAs sharing an SM
       const double rim = (double)(4 * R) / (4 * R + 2 * R + 8);   // own cells / (own + rim loads)
       const double lane = (double)nact / threads;
       const double sync_cost = C > 1 ? 0.85 : 1.0;
       const double par = threads >= 384 ? 1.0 : threads / 384.0;
-      const double regs = R >= 6 ? 0.8 : 1.0;   // measured: R = 4..5 beats 6..8 (register pressure in the adjoint)
-      const double score = busy * rim * lane * sync_cost * par * regs;
+      const double regs = (!nl && R >= 6) ? 0.8 : 1.0;   // measured: R = 4..5 beats 6..8 (register pressure in the adjoint)
+      const double score = (rim * lane * sync_cost * par * regs) / ((double)waves * Hc * per_sm);
       if (score > best_score) { best_score = score; bestC = C; bestR = R; }
     }
   }
@@ -688,17 +494,27 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
   plan->rows_per_thread = bestR;
   plan->threads = threads;
   plan->rows_per_cta = Hc;
-  int ncl = resident_clusters(p->device, bestR, bestC, threads, smem_fwd_bytes(Hc, pitch, p->n_prb),
-                              smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads));
+  plan->nonlinear = nl;
+  const size_t plane = (size_t)p->Nx * p->Ny;
+  int ncl;
+  if (nl) {
+    const int ring = ring_for(Hc, bestR, threads);
+    plan->reserved[0] = ring;
+    plan->smem_fwd = (int)res_nl_smem_fwd(Hc, pitch, p->n_prb);
+    plan->smem_bwd = (int)res_nl_smem_adj(Hc, pitch, p->n_prb, bestR, threads, ring);
+    ncl = res_nl_clusters_cached(p->device, bestR, nl, bestC, threads, plan->smem_fwd, plan->smem_bwd);
+  } else {
+    plan->reserved[0] = RING;
+    plan->smem_fwd = (int)smem_fwd_bytes(Hc, pitch, p->n_prb);
+    plan->smem_bwd = (int)smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads);
+    ncl = resident_clusters(p->device, bestR, bestC, threads, plan->smem_fwd, plan->smem_bwd);
+  }
   if (ncl < 1) return false;
   plan->n_clusters = p->B < ncl ? p->B : ncl;
-  plan->smem_fwd = (int)smem_fwd_bytes(Hc, pitch, p->n_prb);
-  plan->smem_bwd = (int)smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads);
-  plan->history_bytes = (uint64_t)p->B * p->T * bestC * bestR * threads * 16;
-  const size_t plane = (size_t)p->Nx * p->Ny;
+  plan->history_bytes = (uint64_t)p->B * p->T * bestC * (nl ? 2 : 1) * bestR * threads * 16;
   plan->workspace_fwd_bytes = 3 * plane * 4 + 64;
-  plan->workspace_bwd_bytes = (3 + (size_t)plan->n_clusters) * plane * 4 + 64;
-  plan->launches_fwd = 2;
+  plan->workspace_bwd_bytes = (3 + 2 * (size_t)plan->n_clusters) * plane * 4 + 64;
+  plan->launches_fwd = nl ? 1 : 2;
   plan->launches_bwd = 3;
   return true;
 }
@@ -742,7 +558,8 @@ static int launch_cluster(K kernel, const wt_plan& plan, size_t smem, const ResA
     default: wt::set_error("rows_per_thread=%d not instantiated", R_); return WT_EINVAL; \
   }
 
-int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, const float* b, const float* x,
+int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, const float* b, const float* rho,
+                     const float* x,
                      const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_sq, float* u1, float* u2,
                      float* probe_out, float* probe_raw, float* fields_out, void* history, void* workspace,
                      cudaStream_t st) {
@@ -751,21 +568,25 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
   float* a3 = a1 + plane;
   float* gs = a3 + plane;
   int* status = reinterpret_cast<int*>(gs + plane);
-  k_coeff<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(b, c, (int)plane, p->dt, (p->dt * p->dt) / (p->h * p->h), a1,
-                                                            a3, gs);
+  if (!plan.nonlinear)
+    k_coeff<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(b, c, (int)plane, p->dt, (p->dt * p->dt) / (p->h * p->h),
+                                                              a1, a3, gs);
   WT_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
   ResArgs a = {};
   fill_args(p, plan, &a);
+  a.bpml = b; a.clin = c; a.rho = rho; a.s = make_scalars(p); a.ring = plan.reserved[0];
   a.a1 = a1; a.a3 = a3; a.x = x; a.src_ij = src_ij; a.prb_ij = prb_ij; a.prb_sq = prb_sq;
   a.u1 = u1; a.u2 = u2; a.probe_out = probe_out; a.probe_raw = probe_raw; a.fields = fields_out;
   a.vec_fields = (p->Ny % 4 == 0) && (((uintptr_t)fields_out & 15) == 0);
   a.tape = reinterpret_cast<float4*>(history);
   a.status = status;
+  if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st);
   WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R>, plan, plan.smem_fwd, a, st)));
   return WT_OK;
 }
 
-int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, const float* b, const int32_t* src_ij,
+int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, const float* b, const float* rho,
+                      const int32_t* src_ij,
                       const int32_t* prb_ij, const int32_t* prb_sq, const float* grad_probe, const float* probe_raw,
                       const void* history, float* grad_c, float* grad_b, float* grad_rho, float* grad_x,
                       void* workspace, cudaStream_t st) {
@@ -774,9 +595,10 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
   float* a3 = a1 + plane;
   float* gs = a3 + plane;
   float* Gpart = gs + plane;
-  int* status = reinterpret_cast<int*>(Gpart + (size_t)plan.n_clusters * plane);
-  k_coeff<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(b, c, (int)plane, p->dt, (p->dt * p->dt) / (p->h * p->h), a1,
-                                                            a3, gs);
+  int* status = reinterpret_cast<int*>(Gpart + 2 * (size_t)plan.n_clusters * plane);
+  if (!plan.nonlinear)
+    k_coeff<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(b, c, (int)plane, p->dt, (p->dt * p->dt) / (p->h * p->h),
+                                                              a1, a3, gs);
   WT_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
   if (grad_x) WT_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)p->B * p->T * sizeof(float), st));
   ResArgs a = {};
@@ -785,8 +607,18 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
   a.probe_raw = const_cast<float*>(probe_raw); a.grad_probe = grad_probe; a.grad_x = grad_x;
   a.tape = reinterpret_cast<float4*>(const_cast<void*>(history));
   a.Gpart = Gpart; a.status = status;
+  a.bpml = b; a.clin = c; a.rho = rho; a.s = make_scalars(p); a.ring = plan.reserved[0];
+  const unsigned fg = (unsigned)((plane + 255) / 256);
+  if (plan.nonlinear) {
+    WT_TRY(res_nl_launch_adj(plan, a, st));
+    k_finish_grad<<<fg, 256, 0, st>>>(Gpart, nullptr, plan.n_clusters, 2 * plane, plane, grad_c);
+    if (grad_rho) k_finish_grad<<<fg, 256, 0, st>>>(Gpart + plane, nullptr, plan.n_clusters, 2 * plane, plane, grad_rho);
+    if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));   // needs WT_F_NEED_GRAD_B (streaming path)
+    WT_CUDA(cudaGetLastError());
+    return WT_OK;
+  }
   WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st)));
-  k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gpart, gs, plan.n_clusters, plane, grad_c);
+  k_finish_grad<<<fg, 256, 0, st>>>(Gpart, gs, plan.n_clusters, plane, plane, grad_c);
   if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
   if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));
   WT_CUDA(cudaGetLastError());

@@ -1,0 +1,254 @@
+// Device-side building blocks shared by the on-chip kernels (wt_resident.cu, wt_resident_nl.cu).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "wt_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace wt {
+
+constexpr int TB = 64;        // time steps per x / probe staging block
+constexpr int RING = 4;       // tape prefetch depth of the linear adjoint
+constexpr int MAX_PRB = 64;   // probes the resident path stages per CTA
+
+struct ResArgs {
+  int Nx, Ny, B, T;
+  int C, Hc, P4, pitch, nact, runs;
+  int n_src, n_prb, n_clusters;
+  unsigned flags;
+  int vec_fields;            // fields_out may be written with float4
+  const float* a1;
+  const float* a3;
+  const float* x;
+  const int32_t* src_ij;
+  const int32_t* prb_ij;
+  const int32_t* prb_sq;
+  float* u1;
+  float* u2;
+  float* probe_out;
+  float* probe_raw;
+  float* fields;
+  float4* tape;
+  // adjoint only
+  const float* grad_probe;
+  float* grad_x;
+  float* Gpart;              // [n_clusters, nacc, Nx, Ny]
+  int* status;
+  // nonlinear kernels only
+  const float* bpml;
+  const float* clin;
+  const float* rho;
+  int ring;                  // tape prefetch depth
+  Scalars s;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WT_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WT_DONE;\n"
+      "bra WT_WAIT;\n"
+      "WT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- cluster ghost-row exchange -------------------------------------------------------------------
+// Ghost rows travel with st.async: a 16-byte store into the neighbour CTA's shared memory that also counts
+// its bytes on an mbarrier there (complete_tx).  The receiver waits on its own mbarrier only, so the time loop
+// contains no cluster-wide barrier and no cluster-scope fence (which would also wait for the tape stores).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float x, float y, float z, float w, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(
+                   remote_addr),
+               "r"(__float_as_uint(x)), "r"(__float_as_uint(y)), "r"(__float_as_uint(z)), "r"(__float_as_uint(w)),
+               "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WT_WAITC:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WT_DONEC;\n"
+      "bra WT_WAITC;\n"
+      "WT_DONEC:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Per-thread view of the decomposition and of the ghost exchange.
+template <int R>
+struct Lane {
+  int rank, cid, tid, run, j0, lr0, gi0, slab;
+  bool active;
+  bool edge_up, edge_dn;     // my patch borders the slab of rank-1 / rank+1
+  bool arm_up, arm_dn;       // I re-arm the corresponding mbarrier
+  uint32_t push_up, push_dn; // cluster address of the neighbour's ghost row slot (buffer 0)
+  uint32_t rbar_up, rbar_dn; // cluster address of the neighbour's mbarrier my push signals
+  uint64_t* gbar;            // [4] my mbarriers: {from above, from below} x {even, odd publish}.  Two per direction:
+                             // with one, a neighbour that runs ahead could complete the NEXT phase before a slow
+                             // thread of mine has tested the current one, and that thread would wait forever.
+  unsigned row_bytes;
+  unsigned npub;             // publishes so far (phase bookkeeping)
+
+  __device__ __forceinline__ void init(const ResArgs& a, float* fld, uint64_t* bars) {
+    cg::cluster_group cluster = cg::this_cluster();
+    rank = (a.C > 1) ? (int)cluster.block_rank() : 0;
+    cid = blockIdx.x / a.C;
+    tid = threadIdx.x;
+    active = tid < a.nact;
+    run = tid / a.P4;
+    j0 = 4 * (tid - run * a.P4);
+    lr0 = run * R;
+    gi0 = rank * a.Hc + lr0;
+    slab = (a.Hc + 2) * a.pitch;
+    gbar = bars;
+    row_bytes = (unsigned)a.P4 * 16u;
+    npub = 0;
+    edge_up = active && a.C > 1 && run == 0 && rank > 0;
+    edge_dn = active && a.C > 1 && run == a.runs - 1 && rank < a.C - 1;
+    arm_up = edge_up && j0 == 0;
+    arm_dn = edge_dn && j0 == 0;
+    push_up = push_dn = rbar_up = rbar_dn = 0;
+    if (edge_up) {   // my top row is the ghost row BELOW the last row of rank-1
+      push_up = mapa_u32(smem_u32(fld + (a.Hc + 1) * a.pitch + 4 + j0), rank - 1);
+      rbar_up = mapa_u32(smem_u32(bars + 2), rank - 1);
+    }
+    if (edge_dn) {   // my bottom row is the ghost row ABOVE the first row of rank+1
+      push_dn = mapa_u32(smem_u32(fld + 4 + j0), rank + 1);
+      rbar_dn = mapa_u32(smem_u32(bars + 0), rank + 1);
+    }
+    if (tid == 0) {
+      for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (a.C > 1 && rank > 0) { mbar_expect_tx(bars + 0, row_bytes); mbar_expect_tx(bars + 1, row_bytes); }
+      if (a.C > 1 && rank < a.C - 1) { mbar_expect_tx(bars + 2, row_bytes); mbar_expect_tx(bars + 3, row_bytes); }
+    }
+  }
+
+  // Write my R rows into slab buffer `which` (0/1) and push the rim rows to the neighbours.
+  __device__ __forceinline__ void publish(const ResArgs& a, float* fld, int which, const float (&v)[R][4]) {
+    float* buf = fld + which * slab;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      *reinterpret_cast<float4*>(buf + (lr0 + r + 1) * a.pitch + 4 + j0) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+    const uint32_t boff = (uint32_t)(which * slab) * 4u;
+    const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
+    if (edge_up) st_async_v4(push_up + boff, v[0][0], v[0][1], v[0][2], v[0][3], rbar_up + bsel);
+    if (edge_dn) st_async_v4(push_dn + boff, v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3], rbar_dn + bsel);
+  }
+
+  // Wait until the neighbours' rows of the latest publish have landed in my ghost rows; re-arm for the next one.
+  __device__ __forceinline__ void acquire_ghosts() {
+    const unsigned k = npub - 1u, sel = k & 1u, parity = (k >> 1) & 1u;
+    if (edge_up) {
+      mbar_wait_cluster(gbar + sel, parity);
+      if (arm_up) mbar_expect_tx(gbar + sel, row_bytes);        // re-arm for publish k+2
+    }
+    if (edge_dn) {
+      mbar_wait_cluster(gbar + 2 + sel, parity);
+      if (arm_dn) mbar_expect_tx(gbar + 2 + sel, row_bytes);
+    }
+  }
+};
+
+// Which of my 4R cells are sources?  m1: listed at least once, m2: listed at least twice (rnn.py:56-57 adds x
+// once per listing).  Three or more listings of one pixel are not supported by this path (status flag).
+template <int R>
+__device__ __forceinline__ void source_masks(const ResArgs& a, bool active, int gi0, int j0, unsigned& m1,
+                                             unsigned& m2) {
+  m1 = 0; m2 = 0;
+  if (!active) return;
+  for (int s = 0; s < a.n_src; ++s) {
+    int si = a.src_ij[2 * s] - gi0, sj = a.src_ij[2 * s + 1] - j0;
+    if (si >= 0 && si < R && sj >= 0 && sj < 4) {
+      unsigned bit = 1u << (si * 4 + sj);
+      if (m1 & bit) {
+        if (m2 & bit) atomicExch(a.status, 1);
+        m2 |= bit;
+      } else {
+        m1 |= bit;
+      }
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void load_coef(const ResArgs& a, bool active, int gi0, int j0, float (&k1)[R][4],
+                                          float (&k3)[R][4]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int gi = gi0 + r, j = j0 + k;
+      bool ok = active && gi < a.Nx && j < a.Ny;
+      k1[r][k] = ok ? a.a1[(size_t)gi * a.Ny + j] : 0.f;
+      k3[r][k] = ok ? a.a3[(size_t)gi * a.Ny + j] : 0.f;
+    }
+}
+
+// Unscaled 5-point Laplacian of my patch; own cells come from registers, the rim from shared memory.
+template <int R>
+__device__ __forceinline__ void patch_laplacian(int pitch, const float* own, const float (&v)[R][4], float (&lap)[R][4]) {
+  // `own` points at my first row inside the slab buffer
+  const float4 up = *reinterpret_cast<const float4*>(own - pitch);
+  const float4 dn = *reinterpret_cast<const float4*>(own + R * pitch);
+  const float upv[4] = {up.x, up.y, up.z, up.w};
+  const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float lf = own[r * pitch - 1], rt = own[r * pitch + 4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float n = (r == 0) ? upv[k] : v[r - 1][k];
+      float s = (r == R - 1) ? dnv[k] : v[r + 1][k];
+      float w = (k == 0) ? lf : v[r][k - 1];
+      float e = (k == 3) ? rt : v[r][k + 1];
+      lap[r][k] = fmaf(-4.f, v[r][k], (n + s) + (w + e));
+    }
+  }
+}
+
+template <int R>
+constexpr int res_max_threads() {
+  return R <= 1 ? 1024 : R == 2 ? 768 : R == 3 ? 640 : R == 4 ? 512 : R == 5 ? 384 : R == 6 ? 320 : 256;
+}
+
+// host entry points of wt_resident_nl.cu
+int res_nl_max_threads_rt(int R);
+size_t res_nl_smem_fwd(int Hc, int pitch, int n_prb);
+size_t res_nl_smem_adj(int Hc, int pitch, int n_prb, int R, int threads, int ring);
+int res_nl_clusters(int R, int nl, int C, int threads, size_t smem_fwd, size_t smem_bwd);
+int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st);
+int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st);
+
+}  // namespace wt

@@ -1,0 +1,492 @@
+// On-chip kernels for the nonlinear cell (BASELINE config 4): saturable damping b(u) = b_pml + rho*b0/(1+(u/uth)^2)
+// and Kerr-like wave speed c(u) = c_lin + rho*c_nl*u^2, evaluated from u_{t-1} every step (cell.py:94-102).
+//
+// Same decomposition, ghost-row exchange and staging as the linear kernels (wt_resident.cu); differences:
+//   * per-cell registers hold b_pml, c_lin, rho instead of the precomputed a1, a3; the coefficients are rebuilt per
+//     step with the same device functions as the streaming path (wt_common.cuh), so both paths agree bitwise
+//   * the tape holds u_{t-1} AND L(u_{t-1}) per step (8 B/cell); u_{t-2} is read from the next ring stage
+//   * the adjoint accumulates dLoss/dc_lin and the direct dLoss/drho per cluster
+#include "wt_resident.h"
+#include "wt_resident_dev.cuh"
+
+namespace wt {
+
+template <int R>
+constexpr int res_nl_max_threads() {
+  return R <= 1 ? 1024 : R == 2 ? 640 : R == 3 ? 448 : 384;
+}
+
+template <int R>
+__device__ __forceinline__ void load_fields3(const ResArgs& a, bool active, int gi0, int j0, float (&bp)[R][4],
+                                             float (&cl)[R][4], float (&rh)[R][4]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int gi = gi0 + r, j = j0 + k;
+      bool ok = active && gi < a.Nx && j < a.Ny;
+      size_t o = (size_t)gi * a.Ny + j;
+      // cells outside the domain: c = 0 makes a3 = 0, so they stay exactly zero like the linear kernels' padding
+      bp[r][k] = ok ? a.bpml[o] : 0.f;
+      cl[r][k] = ok ? a.clin[o] : 0.f;
+      rh[r][k] = ok ? a.rho[o] : 0.f;
+    }
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int R, bool SAT, bool KERR>
+__global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs a) {
+  extern __shared__ float4 smem4[];
+  const int slab_f = (a.Hc + 2) * a.pitch;
+  float* fld = reinterpret_cast<float*>(smem4);
+  float* xs = fld + 2 * slab_f;
+  float* ps = xs + 2 * TB;
+  int* poff = reinterpret_cast<int*>(ps + 2 * TB * a.n_prb);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(poff + a.n_prb + (a.n_prb & 1));
+
+  Lane<R> L;
+  L.init(a, fld, bars);
+  const int tid = L.tid, NT = blockDim.x;
+  float bp[R][4], cl[R][4], rh[R][4];
+  load_fields3<R>(a, L.active, L.gi0, L.j0, bp, cl, rh);
+  unsigned m1, m2;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
+  for (int p = tid; p < a.n_prb; p += NT) {
+    int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
+    poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * a.pitch + 4 + pj : -1;
+  }
+  for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
+  if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
+  const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
+  const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
+  const size_t tape_step = (size_t)a.C * 2 * R * NT;
+  const size_t plane = (size_t)a.Nx * a.Ny;
+  const Scalars s = a.s;
+
+  for (int b = L.cid; b < a.B; b += a.n_clusters) {
+    float v[R][4], w[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int gi = L.gi0 + r, j = L.j0 + k;
+        bool ok = L.active && gi < a.Nx && j < a.Ny && !(a.flags & WT_F_ZERO_INIT);
+        size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
+        v[r][k] = ok ? a.u1[o] : 0.f;
+        w[r][k] = ok ? a.u2[o] : 0.f;
+      }
+    if (L.active) L.publish(a, fld, 0, v);
+    ++L.npub;
+    const float* xb = a.x + (size_t)b * a.T;
+    for (int i = tid; i < TB && i < a.T; i += NT) xs[i] = xb[i];
+    __syncthreads();
+
+    float4* tape = a.tape ? a.tape + (((size_t)b * a.T) * a.C + L.rank) * 2 * R * NT + tid : nullptr;
+    float* fout = a.fields ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
+
+    auto flush = [&](int blk) {
+      const int t0 = blk * TB, n = min(TB, a.T - t0);
+      const float* src = ps + (blk & 1) * TB * a.n_prb;
+      for (int i = tid; i < n * a.n_prb; i += NT) {
+        int p = i % a.n_prb;
+        if (poff[p] >= 0) {
+          float val = src[i];
+          size_t o = ((size_t)b * a.T + t0 + i / a.n_prb) * a.n_prb + p;
+          if (a.probe_raw) a.probe_raw[o] = val;
+          if (a.probe_out) a.probe_out[o] = a.prb_sq[p] ? val * val : val;
+        }
+      }
+    };
+    auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int t, int blk, int tt) {
+      const float* cur = fld + (t & 1) * L.slab;
+      L.acquire_ghosts();
+      if (t > 0 && my_poff >= 0) ps[(((t - 1) / TB) & 1) * TB * a.n_prb + ((t - 1) % TB) * a.n_prb + tid] = cur[my_poff];
+      if (L.active) {
+        float lap[R][4];
+        patch_laplacian<R>(a.pitch, cur + own, cu, lap);
+        if (tape) {   // the adjoint needs u_{t-1} itself (coefficients) and L(u_{t-1})
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            st_stream(tape + (size_t)r * NT, make_float4(cu[r][0], cu[r][1], cu[r][2], cu[r][3]));
+            st_stream(tape + (size_t)(R + r) * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
+          }
+          tape += tape_step;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float bb, cc, d;
+            wt_nl_bc<SAT, KERR>(s, bp[r][k], cl[r][k], rh[r][k], cu[r][k], bb, cc, d);
+            const CellCoef kc = wt_coef(s, bb, cc);
+            pr[r][k] = wt_update(kc.a1, kc.a3, cu[r][k], pr[r][k], lap[r][k]);
+          }
+        if (m1) {
+          const float xv = xs[(blk & 1) * TB + tt];
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (m1 >> (r * 4 + k) & 1u) pr[r][k] += xv;
+              if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
+            }
+        }
+        L.publish(a, fld, (t + 1) & 1, pr);
+        if (fout) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (L.gi0 + r < a.Nx) {
+              float* f = fout + (size_t)r * a.Ny;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (L.j0 + k < a.Ny) f[k] = pr[r][k];
+            }
+          }
+          fout += plane;
+        }
+      }
+      ++L.npub;
+      __syncthreads();
+    };
+
+    const int nblk = (a.T + TB - 1) / TB;
+    for (int blk = 0; blk < nblk; ++blk) {
+      const int t0 = blk * TB, n = min(TB, a.T - t0);
+      if ((blk + 1) * TB < a.T) {
+        float* dst = xs + ((blk + 1) & 1) * TB;
+        const int t1 = (blk + 1) * TB;
+        for (int i = tid; i < TB && t1 + i < a.T; i += NT) dst[i] = xb[t1 + i];
+      }
+      if (blk >= 2) flush(blk - 2);
+      int tt = 0;
+      for (; tt + 1 < n; tt += 2) {
+        step(v, w, t0 + tt, blk, tt);
+        step(w, v, t0 + tt + 1, blk, tt + 1);
+      }
+      if (tt < n) {
+        step(v, w, t0 + tt, blk, tt);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { float tmp = v[r][k]; v[r][k] = w[r][k]; w[r][k] = tmp; }
+      }
+    }
+    L.acquire_ghosts();
+    if (my_poff >= 0) ps[(((a.T - 1) / TB) & 1) * TB * a.n_prb + ((a.T - 1) % TB) * a.n_prb + tid] = fld[(a.T & 1) * L.slab + my_poff];
+    __syncthreads();
+    for (int blk = max(0, nblk - 2); blk < nblk; ++blk) flush(blk);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int gi = L.gi0 + r, j = L.j0 + k;
+        if (L.active && gi < a.Nx && j < a.Ny) {
+          size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
+          a.u1[o] = v[r][k];
+          a.u2[o] = w[r][k];
+        }
+      }
+    __syncthreads();
+  }
+  if (a.C > 1) cg::this_cluster().sync();
+}
+
+// =================================================================================================
+// adjoint
+// =================================================================================================
+template <int R, bool SAT, bool KERR>
+__global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs a) {
+  const int NT = blockDim.x;
+  const int slab_f = (a.Hc + 2) * a.pitch;
+  const int RG = a.ring;
+  const int stage_f4 = 2 * R * NT;
+  const unsigned stage_bytes = (unsigned)(stage_f4 * sizeof(float4));
+
+  extern __shared__ float4 smem4[];
+  float4* ring = smem4;                                          // [RG][2*R*NT]: u_{t-1} rows, then L(u_{t-1}) rows
+  float* fld = reinterpret_cast<float*>(ring + RG * stage_f4);    // [2][slab]   P = kappa*c^2*q*lambda
+  float* ss = fld + 2 * slab_f;
+  float* gxs = ss + 2 * TB * a.n_prb;
+  int* pown = reinterpret_cast<int*>(gxs + 2 * TB);
+  int* pcell = pown + a.n_prb;
+  uint64_t* full = reinterpret_cast<uint64_t*>(pcell + a.n_prb);  // [RING] (max depth allocated)
+  uint64_t* bars = full + RING;
+
+  Lane<R> L;
+  L.init(a, fld, bars);
+  const int tid = L.tid;
+  float bp[R][4], cl[R][4], rh[R][4];
+  load_fields3<R>(a, L.active, L.gi0, L.j0, bp, cl, rh);
+  unsigned m1, m2;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
+  for (int p = tid; p < a.n_prb; p += NT) {
+    int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
+    bool mine = li >= 0 && li < a.Hc;
+    pown[p] = mine ? (li / R) * a.P4 + pj / 4 : -1;
+    pcell[p] = mine ? (li % R) * 4 + (pj & 3) : 0;
+  }
+  for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
+  for (int i = tid; i < 2 * TB; i += NT) gxs[i] = 0.f;
+  if (tid == 0) {
+    for (int q = 0; q < RING; ++q) mbar_init(full + q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
+  bool has_probe = false;
+  for (int p = 0; p < a.n_prb; ++p) has_probe |= (pown[p] == tid);
+  const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
+  const Scalars s = a.s;
+
+  float Gc[R][4], Gr[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { Gc[r][k] = 0.f; Gr[r][k] = 0.f; }
+
+  unsigned it_global = 0;
+  for (int b = L.cid; b < a.B; b += a.n_clusters) {
+    float lam[R][4], c2[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { lam[r][k] = 0.f; c2[r][k] = 0.f; }
+
+    auto tape_ptr = [&](int t) { return a.tape + ((((size_t)b * a.T + t) * a.C + L.rank) * 2 * R) * NT; };
+    auto stage_seeds = [&](int blk) {
+      const int t0 = blk * TB, n = min(TB, a.T - t0);
+      float* dst = ss + (blk & 1) * TB * a.n_prb;
+      for (int i = tid; i < n * a.n_prb; i += NT) {
+        int p = i % a.n_prb;
+        size_t o = ((size_t)b * a.T + t0 + i / a.n_prb) * a.n_prb + p;
+        float g = a.grad_probe[o];
+        if (a.prb_sq[p]) g *= 2.f * a.probe_raw[o];
+        dst[i] = g;
+      }
+    };
+    auto flush_gx = [&](int blk) {
+      const int t0 = blk * TB, n = min(TB, a.T - t0);
+      float* src = gxs + (blk & 1) * TB;
+      for (int i = tid; i < n; i += NT) {
+        float sv = src[i];
+        src[i] = 0.f;
+        if (sv != 0.f) atomicAdd(a.grad_x + (size_t)b * a.T + t0 + i, sv);
+      }
+    };
+    if (tid == 0) {
+      for (int q = 0; q < RG && q < a.T; ++q) {
+        unsigned slot = (it_global + q) % RG;
+        mbar_expect_tx(full + slot, stage_bytes);
+        bulk_g2s(ring + slot * stage_f4, tape_ptr(a.T - 1 - q), stage_bytes, full + slot);
+      }
+    }
+    stage_seeds((a.T - 1) / TB);
+    __syncthreads();
+
+    for (int t = a.T - 1, it = 0; t >= 0; --t, ++it) {
+      const int blk = t / TB, tt = t - blk * TB;
+      float* cur = fld + (it & 1) * L.slab;
+      if ((t == a.T - 1 || tt == TB - 1) && blk > 0) stage_seeds(blk - 1);
+      if (a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
+      const unsigned gi = it_global + it;
+      const unsigned slot = gi % RG, parity = (gi / RG) & 1u;
+      const unsigned slot2 = (gi + 1) % RG, parity2 = ((gi + 1) / RG) & 1u;   // stage of step t-1: its u is my u_{t-2}
+      float pv[R][4], g1[R][4], g2[R][4];
+      if (L.active) {
+        if (has_probe) {
+          for (int p = 0; p < a.n_prb; ++p)
+            if (pown[p] == tid) {
+              const float sv = ss[(blk & 1) * TB * a.n_prb + tt * a.n_prb + p];
+              const int pc = pcell[p];
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (pc == r * 4 + k) lam[r][k] += sv;
+            }
+        }
+        if (a.grad_x && m1) {
+          float sv = 0.f;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (m1 >> (r * 4 + k) & 1u) sv += lam[r][k];
+              if (m2 >> (r * 4 + k) & 1u) sv += lam[r][k];
+            }
+          atomicAdd(gxs + (blk & 1) * TB + tt, sv);
+        }
+        mbar_wait(full + slot, parity);
+        if (t > 0) mbar_wait(full + slot2, parity2);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 u1v = ring[slot * stage_f4 + r * NT + tid];
+          const float4 lpv = ring[slot * stage_f4 + (R + r) * NT + tid];
+          float4 u2v = make_float4(0.f, 0.f, 0.f, 0.f);      // t = 0: u_{-2} is the zero initial field (WT_F_ZERO_INIT)
+          if (t > 0) u2v = ring[slot2 * stage_f4 + r * NT + tid];
+          const float u1a[4] = {u1v.x, u1v.y, u1v.z, u1v.w};
+          const float lpa[4] = {lpv.x, lpv.y, lpv.z, lpv.w};
+          const float u2a[4] = {u2v.x, u2v.y, u2v.z, u2v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float u1 = u1a[k], u2 = u2a[k];
+            float bb, cc, d;
+            wt_nl_bc<SAT, KERR>(s, bp[r][k], cl[r][k], rh[r][k], u1, bb, cc, d);
+            const float beta = bb * s.dt;
+            const float q = 1.f / (1.f + beta);
+            const float ql = q * lam[r][k];
+            const float kl = s.kappa * lpa[k];
+            const float S = fmaf(cc * cc, kl, 2.f * (u1 - u2));
+            const float g_b = -s.dt * q * S * ql;            // cell.py:33-34
+            const float g_c = 2.f * cc * kl * ql;             // cell.py:36
+            float gu1 = 2.f * ql;                             // own-cell part of cell.py:39-40
+            if (SAT) {
+              const float iu = s.inv_uth;
+              Gr[r][k] = fmaf(g_b, s.b0 / d, Gr[r][k]);
+              gu1 = fmaf(g_b, rh[r][k] * s.b0 * (-2.f * u1 * iu * iu) / (d * d), gu1);
+            }
+            if (KERR) {
+              Gr[r][k] = fmaf(g_c, s.c_nl * u1 * u1, Gr[r][k]);
+              gu1 = fmaf(g_c, 2.f * rh[r][k] * s.c_nl * u1, gu1);
+            }
+            Gc[r][k] += g_c;
+            pv[r][k] = s.kappa * cc * cc * ql;
+            g1[r][k] = gu1;
+            g2[r][k] = (beta - 1.f) * ql;                     // cell.py:42
+          }
+        }
+        L.publish(a, fld, it & 1, pv);
+      }
+      ++L.npub;
+      __syncthreads();
+      if (tid == 0 && it + RG < a.T) {
+        mbar_expect_tx(full + slot, stage_bytes);
+        bulk_g2s(ring + slot * stage_f4, tape_ptr(t - RG), stage_bytes, full + slot);
+      }
+      L.acquire_ghosts();
+      if (L.active) {
+        float lapP[R][4];
+        patch_laplacian<R>(a.pitch, cur + own, pv, lapP);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            lam[r][k] = c2[r][k] + (g1[r][k] + lapP[r][k]);
+            c2[r][k] = g2[r][k];
+          }
+      }
+    }
+    it_global += (unsigned)a.T;
+    __syncthreads();
+    if (a.grad_x) flush_gx(0);
+    __syncthreads();
+  }
+  const size_t plane = (size_t)a.Nx * a.Ny;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int gi = L.gi0 + r, j = L.j0 + k;
+      if (L.active && gi < a.Nx && j < a.Ny) {
+        size_t o = ((size_t)L.cid * 2) * plane + (size_t)gi * a.Ny + j;
+        a.Gpart[o] = Gc[r][k];
+        a.Gpart[o + plane] = Gr[r][k];
+      }
+    }
+  if (a.C > 1) cg::this_cluster().sync();
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+int res_nl_max_threads_rt(int R) {
+  switch (R) {
+    case 1: return 1024;
+    case 2: return 640;
+    case 3: return 448;
+    case 4: return 384;
+    default: return 0;
+  }
+}
+
+size_t res_nl_smem_fwd(int Hc, int pitch, int n_prb) {
+  return (size_t)2 * (Hc + 2) * pitch * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)(n_prb + 1) * 4 + 4 * 8 + 16;
+}
+size_t res_nl_smem_adj(int Hc, int pitch, int n_prb, int R, int threads, int ring) {
+  return (size_t)ring * 2 * R * threads * 16 + (size_t)2 * (Hc + 2) * pitch * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
+         (size_t)2 * n_prb * 4 + 8 + RING * 8 + 4 * 8 + 16;
+}
+
+template <typename K>
+static int nl_active_clusters(K kernel, int C, int threads, size_t smem) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (C > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C * 1024);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+#define WT_NL_CASE(R_, NL_, CALLF)                                                          \
+  if (R == R_ && nl == NL_) { constexpr int RR = R_; constexpr bool SAT = (NL_ & 1) != 0, KERR = (NL_ & 2) != 0; CALLF; }
+#define WT_NL_ALL(CALLF)                                                                    \
+  WT_NL_CASE(1, 1, CALLF) WT_NL_CASE(1, 2, CALLF) WT_NL_CASE(1, 3, CALLF)                  \
+  WT_NL_CASE(2, 1, CALLF) WT_NL_CASE(2, 2, CALLF) WT_NL_CASE(2, 3, CALLF)                  \
+  WT_NL_CASE(3, 1, CALLF) WT_NL_CASE(3, 2, CALLF) WT_NL_CASE(3, 3, CALLF)                  \
+  WT_NL_CASE(4, 1, CALLF) WT_NL_CASE(4, 2, CALLF) WT_NL_CASE(4, 3, CALLF)
+
+int res_nl_clusters(int R, int nl, int C, int threads, size_t smem_fwd, size_t smem_bwd) {
+  int nf = 0, nb = 0;
+  WT_NL_ALL((nf = nl_active_clusters(k_res_fwd_nl<RR, SAT, KERR>, C, threads, smem_fwd),
+             nb = nl_active_clusters(k_res_adj_nl<RR, SAT, KERR>, C, threads, smem_bwd)))
+  return nf < nb ? nf : nb;
+}
+
+template <typename K>
+static int nl_launch(K kernel, const wt_plan& plan, size_t smem, const ResArgs& a, cudaStream_t st) {
+  WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (plan.cluster > 8) WT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.n_clusters * plan.cluster);
+  cfg.blockDim = dim3(plan.threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WT_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
+  return WT_OK;
+}
+
+int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
+  const int R = plan.rows_per_thread, nl = plan.nonlinear;
+  int rc = WT_EINVAL;
+  WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR>, plan, plan.smem_fwd, a, st)))
+  if (rc == WT_EINVAL) set_error("nonlinear on-chip kernel R=%d nl=%d not instantiated", R, nl);
+  return rc;
+}
+
+int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
+  const int R = plan.rows_per_thread, nl = plan.nonlinear;
+  int rc = WT_EINVAL;
+  WT_NL_ALL((rc = nl_launch(k_res_adj_nl<RR, SAT, KERR>, plan, plan.smem_bwd, a, st)))
+  if (rc == WT_EINVAL) set_error("nonlinear on-chip kernel R=%d nl=%d not instantiated", R, nl);
+  return rc;
+}
+
+}  // namespace wt

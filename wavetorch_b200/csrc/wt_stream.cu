@@ -269,12 +269,12 @@ __global__ void k_scale_carry(float* __restrict__ lam, const float* __restrict__
     lam[i] = (1.f - a1[i % plane]) * lam[i];
 }
 
-__global__ void k_finish_grad(const float* __restrict__ G, const float* __restrict__ gscale, int n_part, size_t plane,
-                              float* __restrict__ grad_c) {
+__global__ void k_finish_grad(const float* __restrict__ G, const float* __restrict__ gscale, int n_part, size_t stride,
+                              size_t plane, float* __restrict__ grad_c) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= plane) return;
   float s = 0.f;
-  for (int k = 0; k < n_part; ++k) s += G[(size_t)k * plane + i];
+  for (int k = 0; k < n_part; ++k) s += G[(size_t)k * stride + i];
   grad_c[i] = gscale ? gscale[i] * s : s;
 }
 
@@ -598,7 +598,7 @@ int stream_backward(const wt_problem* p, const float* c, const float* b, const f
       float* tmp = l1; l1 = l2; l2 = tmp;   // l1 = lambda_{t-1} (unseeded), l2 = lambda_t
     }
     WT_CUDA(cudaGetLastError());
-    k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gc, gs, 1, plane, grad_c);
+    k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gc, gs, 1, plane, plane, grad_c);
     if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
     if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));
     if (chained) {
@@ -634,9 +634,9 @@ int stream_backward(const wt_problem* p, const float* c, const float* b, const f
     float* tmp = l1; l1 = l2; l2 = tmp;     // l1 = carry1 for step t-1, l2 = carry2
   }
   WT_CUDA(cudaGetLastError());
-  k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gc, nullptr, 1, plane, grad_c);
-  if (grad_b) k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gb, nullptr, 1, plane, grad_b);
-  if (grad_rho) k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gr, nullptr, 1, plane, grad_rho);
+  k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gc, nullptr, 1, plane, plane, grad_c);
+  if (grad_b) k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gb, nullptr, 1, plane, plane, grad_b);
+  if (grad_rho) k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gr, nullptr, 1, plane, plane, grad_rho);
   if (chained && l1 != adj1) k_swap<<<592, 256, 0, st>>>(adj1, adj2, field);
   WT_CUDA(cudaGetLastError());
   return WT_OK;

@@ -27,7 +27,7 @@ int step_backward(const wt_problem* p, const float* b, int bb, const float* c, i
 // shared small kernels used by the resident path as well
 __global__ void k_coeff(const float* __restrict__ b, const float* __restrict__ c, int n, double dt, double kappa,
                         float* __restrict__ a1, float* __restrict__ a3, float* __restrict__ gscale);
-__global__ void k_finish_grad(const float* __restrict__ G, const float* __restrict__ gscale, int n_part, size_t plane,
-                              float* __restrict__ grad_c);
+__global__ void k_finish_grad(const float* __restrict__ G, const float* __restrict__ gscale, int n_part, size_t stride,
+                              size_t plane, float* __restrict__ grad_c);
 
 }  // namespace wt
