@@ -347,3 +347,60 @@ def test_wavecell_step_api_matches_rnn():
             outs.append(torch.stack([p(h1) for p in m.probes], dim=-1))
         stepped = torch.stack(outs, dim=1)
     assert rel_l2(stepped.cpu().numpy(), fused.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("name,b0,uth,cnl", [("small_linear", 0, 0, 0), ("small_both", 0.4, 0.7, -0.12)])
+@pytest.mark.parametrize("S,chunk", [(7, 0), (16, 2), (47, 1)])
+def test_checkpointed_adjoint_matches_reference(name, b0, uth, cnl, S, chunk):
+    """Checkpoint-and-recompute (segments of S steps, adjoint state chained through adj1/adj2, optional batch chunks)
+    gives the same outputs and gradients as the reference."""
+    g = load_golden(name)
+    m = _small_model(g, b0, uth, cnl, 0)
+    m.checkpoint_every, m.batch_chunk = S, chunk
+    x = torch.tensor(g["x_f64"], dtype=torch.float32, device=DEV, requires_grad=True)
+    out = m(x)
+    (out * torch.tensor(g["w_f64"], dtype=torch.float32, device=DEV)).sum().backward()
+    assert rel_l2(out.detach().cpu().numpy(), g["out_f32"]) < 1e-5
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f32"]) < 1e-4
+    assert rel_l2(x.grad.cpu().numpy(), g["x_grad_f32"]) < 1e-4
+
+
+def test_checkpointed_vowel_config_matches_store_all():
+    """Config-3 geometry, B=6, T=1000: S=45 checkpoints vs the on-chip store-all path and the reference fixture."""
+    g = load_golden("vowel_linear")
+    m = _vowel_model()
+    m.checkpoint_every = 45
+    x = torch.tensor(g["x_f64"], dtype=torch.float32, device=DEV)
+    out = m(x)
+    _loss_head(out, torch.arange(6, device=DEV) % 3).backward()
+    assert rel_l2(out.detach().cpu().numpy(), g["out_f32"]) < 1e-5
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f32"]) < 1e-4
+
+
+def test_config5_truncated_large_grid_against_oracle():
+    """BASELINE config 5 shape, truncated: 512x384 crop of the large-grid setup, B=2, T=64, streaming path,
+    with checkpoints every 24 steps, against the float64 oracle."""
+    Nx, Ny, B, T, N = 512, 384, 2, 64, 20
+    ii, jj = np.mgrid[0:Nx, 0:Ny]
+    rho0 = (0.5 + 0.5 * np.sin(2 * np.pi * ii / 97) * np.cos(2 * np.pi * jj / 61)).astype(np.float32)
+    geom = wt.WaveGeometryFreeForm((Nx, Ny), 1.4283556979968262, 1.0, 0.5, abs_N=N, abs_sig=3.0, abs_p=4.0,
+                                   rho=torch.tensor(rho0))
+    src = wt.WaveSource(60, Ny // 2)
+    prb = [wt.WaveIntensityProbe(100, Ny // 2 + 20 * k) for k in (-1, 0, 1)]
+    m = wt.WaveRNN(wt.WaveCell(1.0, geom), [src], prb).to(DEV)
+    m.checkpoint_every = 24
+    x0 = wo.synthetic_vowels(B, T)
+    x = torch.tensor(x0, device=DEV)
+    out = m(x)
+    w = np.random.RandomState(1).rand(B, T, 3).astype(np.float32)
+    (out * torch.tensor(w, device=DEV)).sum().backward()
+    b = wo.pml_damping(Nx, Ny, N, 3.0, 4.0, np.float64)
+    rho = wo.constrain_to_design_region(rho0.astype(np.float64), None, b)
+    c = wo.wave_speed(rho, 1.0, 0.5)
+    srcs = np.array([[60, Ny // 2]]); prbs = np.array([[100, Ny // 2 + 20 * k] for k in (-1, 0, 1)])
+    f = wo.forward(c, b, rho, x0.astype(np.float64), srcs, prbs, 1.0, 1.4283556979968262, keep_fields=True)
+    o = wo.probe_outputs(f["raw"], [True] * 3)
+    a = wo.adjoint(c, b, rho, x0.astype(np.float64), srcs, prbs, [True] * 3, 1.0, 1.4283556979968262, w.astype(np.float64), f)
+    grho = wo.wave_speed_vjp(rho, a["grad_c"], 1.0, 0.5)
+    assert rel_l2(out.detach().cpu().numpy(), o) < 1e-5
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), grho) < 1e-4

@@ -47,6 +47,145 @@ class LoopSpec:
     flags: int = 0
     cluster: int = 0
     rows_per_thread: int = 0
+    checkpoint_every: int = 0   # > 0: keep only (u_t, u_{t-1}) every S steps and recompute each segment's tape in backward
+    batch_chunk: int = 0        # > 0: process the batch in chunks of this many waveforms (bounds the tape / checkpoints)
+
+
+def _call_forward(lib, prob, dev, c32, b32, rho32, x32, spec, u1, u2, probe_out, probe_raw, fields, hist, ws):
+    with torch.cuda.device(dev):
+        st = lib.wt_forward(ctypes.byref(prob), _lib.ptr(c32), _lib.ptr(b32), _lib.ptr(rho32), _lib.ptr(x32),
+                            _lib.ptr(spec.src_ij), _lib.ptr(spec.prb_ij), _lib.ptr(spec.prb_sq), _lib.ptr(u1),
+                            _lib.ptr(u2), _lib.ptr(probe_out), _lib.ptr(probe_raw), _lib.ptr(fields),
+                            _lib.ptr(hist), hist.numel() if hist is not None else 0, _lib.ptr(ws), ws.numel(),
+                            _lib.stream_ptr(dev))
+    _lib.check(st, "wt_forward")
+
+
+def _dev_index(dev):
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+class _CheckpointedLoop(torch.autograd.Function):
+    """Same contract as _WaveLoop, with O(T/S + S) instead of O(T) field storage: the forward keeps the pair
+    (u_t, u_{t-1}) every S steps; the backward re-runs each segment with a tape and chains the adjoint state between
+    segments through wt_backward's adj1/adj2 (checkpoint-and-recompute for long T / large grids).
+    Runs on the streaming kernels; the batch can additionally be processed in chunks."""
+
+    @staticmethod
+    def _segments(T, S):
+        return [(s0, min(s0 + S, T)) for s0 in range(0, T, S)]
+
+    @staticmethod
+    def _problem(spec, Nx, Ny, B, T, dev, zero_init, need_b):
+        flags = (spec.flags | _lib.WT_F_FORCE_STREAM) & ~_lib.WT_F_ZERO_INIT
+        if zero_init:
+            flags |= _lib.WT_F_ZERO_INIT
+        if need_b:
+            flags |= _lib.WT_F_NEED_GRAD_B
+        n_src, n_prb = spec.src_ij.shape[0], spec.prb_ij.shape[0]
+        return _lib.make_problem(Nx, Ny, B, T, n_src, n_prb, spec.dt, spec.h, spec.b0, spec.uth, spec.c_nl, flags,
+                                 _dev_index(dev))
+
+    @staticmethod
+    def forward(ctx, x, c, b, rho, spec):
+        lib = _lib.load()
+        _require_cuda(x, "the input waveform x")
+        _require_cuda(c, "the wave speed c")
+        if spec.output_fields:
+            raise NotImplementedError("wavetorch_b200: output_fields is not available with checkpoint_every > 0")
+        dev = x.device
+        x32, c32, b32, rho32 = _f32(x, "x"), _f32(c, "c"), _f32(b, "b"), _f32(rho, "rho")
+        B, T = x32.shape
+        Nx, Ny = c32.shape
+        n_prb = spec.prb_ij.shape[0]
+        need = ctx.needs_input_grad
+        want_grad = any(need[:4]) and T > 0
+        segs = _CheckpointedLoop._segments(T, int(spec.checkpoint_every))
+        bc = int(spec.batch_chunk) if spec.batch_chunk else B
+        chunks = [(b0, min(b0 + bc, B)) for b0 in range(0, B, bc)]
+        out = torch.empty((B, T, n_prb), device=dev, dtype=torch.float32)
+        ckpts = {}
+        for ci, (b0, b1) in enumerate(chunks):
+            nb = b1 - b0
+            u1 = torch.empty((nb, Nx, Ny), device=dev, dtype=torch.float32)
+            u2 = torch.empty_like(u1)
+            for k, (s0, s1) in enumerate(segs):
+                if k > 0 and want_grad:
+                    ckpts[(ci, k)] = (u1.clone(), u2.clone())
+                prob = _CheckpointedLoop._problem(spec, Nx, Ny, nb, s1 - s0, dev, k == 0, False)
+                plan = _lib.query_plan(prob)
+                ws = torch.empty(max(int(plan.workspace_fwd_bytes), 16), device=dev, dtype=torch.uint8)
+                po = torch.empty((nb, s1 - s0, n_prb), device=dev, dtype=torch.float32)
+                _call_forward(lib, prob, dev, c32, b32, rho32, x32[b0:b1, s0:s1].contiguous(), spec, u1, u2, po, None, None,
+                              None, ws)
+                _lib.count_launches(plan.launches_fwd)
+                out[b0:b1, s0:s1] = po
+        if want_grad:
+            ctx.spec, ctx.segs, ctx.chunks, ctx.ckpts = spec, segs, chunks, ckpts
+            ctx.saved = (x32, c32, b32, rho32)
+            ctx.dtypes = (x.dtype, c.dtype, b.dtype, rho.dtype if rho is not None else None)
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        spec, segs, chunks, ckpts = ctx.spec, ctx.segs, ctx.chunks, ctx.ckpts
+        x32, c32, b32, rho32 = ctx.saved
+        dev = c32.device
+        B, T = x32.shape
+        Nx, Ny = c32.shape
+        n_prb = spec.prb_ij.shape[0]
+        need = ctx.needs_input_grad
+        nonlinear = spec.b0 > 0 or spec.c_nl != 0
+        g = grad_out.detach().to(torch.float32)
+        z = lambda: torch.zeros((Nx, Ny), device=dev, dtype=torch.float32)
+        grad_c, grad_b, grad_rho = z(), (z() if need[2] else None), (z() if (need[3] and nonlinear) else None)
+        tc, tb_, tr = z(), (z() if need[2] else None), (z() if (need[3] and nonlinear) else None)
+        grad_x = torch.zeros((B, T), device=dev, dtype=torch.float32) if need[0] else None
+        for ci, (b0, b1) in enumerate(chunks):
+            nb = b1 - b0
+            adj1 = torch.zeros((nb, Nx, Ny), device=dev, dtype=torch.float32)
+            adj2 = torch.zeros_like(adj1)
+            for k in range(len(segs) - 1, -1, -1):
+                s0, s1 = segs[k]
+                prob = _CheckpointedLoop._problem(spec, Nx, Ny, nb, s1 - s0, dev, k == 0, bool(need[2]))
+                plan = _lib.query_plan(prob)
+                if k > 0:
+                    u1, u2 = (t.clone() for t in ckpts[(ci, k)])
+                else:
+                    u1 = torch.empty((nb, Nx, Ny), device=dev, dtype=torch.float32)
+                    u2 = torch.empty_like(u1)
+                ws = torch.empty(max(int(plan.workspace_fwd_bytes), int(plan.workspace_bwd_bytes), 16), device=dev,
+                                 dtype=torch.uint8)
+                hist = torch.empty(max(int(plan.history_bytes), 16), device=dev, dtype=torch.uint8)
+                po = torch.empty((nb, s1 - s0, n_prb), device=dev, dtype=torch.float32)
+                praw = torch.empty_like(po)
+                _call_forward(lib, prob, dev, c32, b32, rho32, x32[b0:b1, s0:s1].contiguous(), spec, u1, u2, po, praw, None,
+                              hist, ws)
+                gseg = g[b0:b1, s0:s1].contiguous()
+                gx = torch.empty((nb, s1 - s0), device=dev, dtype=torch.float32) if need[0] else None
+                with torch.cuda.device(dev):
+                    st = lib.wt_backward(ctypes.byref(prob), _lib.ptr(c32), _lib.ptr(b32), _lib.ptr(rho32),
+                                         _lib.ptr(spec.src_ij), _lib.ptr(spec.prb_ij), _lib.ptr(spec.prb_sq),
+                                         _lib.ptr(gseg), _lib.ptr(praw), None, _lib.ptr(hist), hist.numel(),
+                                         _lib.ptr(adj1), _lib.ptr(adj2), _lib.ptr(tc), _lib.ptr(tb_), _lib.ptr(tr),
+                                         _lib.ptr(gx), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+                _lib.check(st, "wt_backward")
+                _lib.count_launches(plan.launches_fwd + plan.launches_bwd)
+                grad_c += tc
+                if grad_b is not None:
+                    grad_b += tb_
+                if grad_rho is not None:
+                    grad_rho += tr
+                if gx is not None:
+                    grad_x[b0:b1, s0:s1] = gx
+                del hist, u1, u2
+        ctx.ckpts = None
+        xd, cd, bd, rd = ctx.dtypes
+        if need[3] and grad_rho is None:
+            grad_rho = z()
+        return (grad_x.to(xd) if need[0] else None, grad_c.to(cd) if need[1] else None,
+                grad_b.to(bd) if need[2] else None, grad_rho.to(rd) if need[3] else None, None)
 
 
 class _WaveLoop(torch.autograd.Function):
@@ -130,6 +269,8 @@ class _WaveLoop(torch.autograd.Function):
 
 def wave_rnn(x, c, b, rho, spec):
     """Run the fused time loop.  x [B,T]; c, b, rho [Nx,Ny]; returns [B,T,n_prb] (or [B,T,Nx,Ny])."""
+    if spec.checkpoint_every and spec.checkpoint_every > 0 and spec.checkpoint_every < x.shape[1]:
+        return _CheckpointedLoop.apply(x, c, b, rho, spec)
     return _WaveLoop.apply(x, c, b, rho, spec)
 
 

@@ -21,6 +21,9 @@ class WaveRNN(torch.nn.Module):
         self.cluster = 0
         self.rows_per_thread = 0
         self.plan_flags = 0
+        # memory/recompute trade-off for training long sequences or large grids (0 = keep the whole tape)
+        self.checkpoint_every = 0
+        self.batch_chunk = 0
 
     # ------------------------------------------------------------------
     def _pixel_tables(self, device):
@@ -85,7 +88,8 @@ class WaveRNN(torch.nn.Module):
         flags = self.plan_flags | (_lib.WT_F_FORCE_STREAM if tab["force_stream"] else 0)
         spec = LoopSpec(src_ij=tab["src_ij"], prb_ij=tab["prb_ij"], prb_sq=tab["prb_sq"], dt=s["dt"], h=geom._h_host,
                         b0=s["b0"], uth=s["uth"], c_nl=s["c_nl"], output_fields=fields, flags=flags,
-                        cluster=self.cluster, rows_per_thread=self.rows_per_thread)
+                        cluster=self.cluster, rows_per_thread=self.rows_per_thread,
+                        checkpoint_every=self.checkpoint_every, batch_chunk=self.batch_chunk)
         y = wave_rnn(x, c, b, rho, spec)
         if fields or tab["scalar_probes"]:
             return y
