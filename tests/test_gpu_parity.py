@@ -404,3 +404,66 @@ def test_config5_truncated_large_grid_against_oracle():
     grho = wo.wave_speed_vjp(rho, a["grad_c"], 1.0, 0.5)
     assert rel_l2(out.detach().cpu().numpy(), o) < 1e-5
     assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), grho) < 1e-4
+
+
+@pytest.mark.parametrize("b0,uth,cnl", [(0.0, 0.0, 0.0), (0.3, 0.7, -0.1)])
+@pytest.mark.parametrize("nslabs,halo", [(2, 8), (3, 5), (4, 12)])
+def test_domain_decomposition_virtual_ranks(b0, uth, cnl, nslabs, halo):
+    """Row-slab domain decomposition with halo depth = temporal block, all slabs in one process:
+    identical probe series, rho.grad and x.grad as the undecomposed run."""
+    from wavetorch_b200.domain import DomainDecomposedWaveRNN
+    Nx, Ny, B, T, N = 96, 72, 2, 61, 6
+    rng = np.random.RandomState(3)
+    rho0 = rng.rand(Nx, Ny).astype(np.float32)
+    def build():
+        geom = wt.WaveGeometryFreeForm((Nx, Ny), 1.0, 1.0, 0.6, abs_N=N, abs_sig=3.0, abs_p=3.0, beta=10.0, rho=torch.tensor(rho0))
+        src = [wt.WaveSource(N + 4, Ny // 2), wt.WaveSource(47, 20)]
+        prb = [wt.WaveIntensityProbe(Nx - N - 4, 20), wt.WaveProbe(48, 50), wt.WaveIntensityProbe(23, 40), wt.WaveProbe(71, 30)]
+        return wt.WaveRNN(wt.WaveCell(0.6, geom, satdamp_b0=b0, satdamp_uth=uth, c_nl=cnl), src, prb).to(DEV)
+    x0 = (0.2 * rng.randn(B, T)).astype(np.float32)
+    w = torch.tensor(rng.randn(B, T, 4).astype(np.float32), device=DEV)
+    ref = build(); ref.plan_flags = _lib.WT_F_FORCE_STREAM
+    xr = torch.tensor(x0, device=DEV, requires_grad=True)
+    out_ref = ref(xr)
+    (out_ref * w).sum().backward()
+    m = build()
+    dd = DomainDecomposedWaveRNN(m, halo=halo, virtual_ranks=nslabs)
+    xd = torch.tensor(x0, device=DEV, requires_grad=True)
+    out = dd(xd)
+    (out * w).sum().backward()
+    assert rel_l2(out.detach().cpu().numpy(), out_ref.detach().cpu().numpy()) < 2e-6
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), ref.cell.geom.rho.grad.cpu().numpy()) < 2e-5
+    assert rel_l2(xd.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("shape,T,K,R", [((512, 384), 64, 4, 4), ((200, 252), 37, 4, 2), ((130, 128), 50, 8, 4), ((97, 64), 23, 8, 3)])
+def test_temporally_blocked_forward_matches_per_step_kernels(shape, T, K, R, monkeypatch):
+    """wt_tile.cu (K steps per HBM round trip) against the one-launch-per-step streaming kernels: probes, final
+    fields, and the gradient obtained from the tape it writes."""
+    Nx, Ny = shape
+    B, N = 3, 8
+    rng = np.random.RandomState(Nx + Ny)
+    rho0 = rng.rand(Nx, Ny).astype(np.float32)
+    def build():
+        geom = wt.WaveGeometryFreeForm((Nx, Ny), 1.0, 1.0, 0.6, abs_N=N, abs_sig=3.0, abs_p=3.0, beta=10.0, rho=torch.tensor(rho0))
+        src = [wt.WaveSource(39, min(119, Ny - 2)), wt.WaveSource(40, min(120, Ny - 1)), wt.WaveSource(40, min(120, Ny - 1)), wt.WaveLineSource(N + 2, 10, N + 2, 30)]
+        prb = [wt.WaveIntensityProbe(Nx - N - 2, Ny // 3), wt.WaveProbe(40, min(119, Ny - 2)), wt.WaveProbe(min(79, Nx - 1), min(121, Ny - 1)),
+               wt.WaveIntensityProbe(0, 0), wt.WaveProbe(Nx - 1, Ny - 1)]
+        m = wt.WaveRNN(wt.WaveCell(0.6, geom), src, prb).to(DEV)
+        m.plan_flags = _lib.WT_F_FORCE_STREAM
+        return m
+    x0 = (0.3 * rng.randn(B, T)).astype(np.float32)
+    w = torch.tensor(rng.randn(B, T, 5).astype(np.float32), device=DEV)
+    monkeypatch.setenv("WT_NO_TILE", "1")
+    ref = build()
+    out_ref = ref(torch.tensor(x0, device=DEV))
+    (out_ref * w).sum().backward()
+    monkeypatch.setenv("WT_NO_TILE", "0")
+    monkeypatch.setenv("WT_TILE_MIN_CELLS", "0")
+    monkeypatch.setenv("WT_TILE_K", str(K))
+    monkeypatch.setenv("WT_TILE_R", str(R))
+    m = build()
+    out = m(torch.tensor(x0, device=DEV))
+    (out * w).sum().backward()
+    assert torch.equal(out, out_ref)          # same arithmetic, same association order: bitwise equal
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), ref.cell.geom.rho.grad.cpu().numpy()) < 1e-6

@@ -9,6 +9,7 @@
 // operators.py:5-11, source.py:15-22, probe.py:14-27.
 #include "wt_common.cuh"
 #include "wt_stream.h"
+#include "wt_tile.h"
 
 namespace wt {
 
@@ -458,10 +459,13 @@ size_t stream_tape_bytes(const wt_problem* p) {
   return general ? field * ((size_t)p->T + 1) : field * (size_t)p->T;
 }
 
-size_t stream_ws_fwd_bytes(const wt_problem* p) {
+static size_t stream_ws_fwd_base(const wt_problem* p) {
   size_t plane = (size_t)p->Nx * p->Ny;
-  return 3 * plane * sizeof(float) + (size_t)(p->n_src + p->n_prb + 4) * sizeof(int32_t) + 256;
+  size_t n = 3 * plane * sizeof(float) + (size_t)(p->n_src + p->n_prb + 4) * sizeof(int32_t) + 256;
+  return (n + 255) & ~(size_t)255;
 }
+
+size_t stream_ws_fwd_bytes(const wt_problem* p) { return stream_ws_fwd_base(p) + tile_extra_ws_bytes(p); }
 
 size_t stream_ws_bwd_bytes(const wt_problem* p) {
   size_t plane = (size_t)p->Nx * p->Ny;
@@ -510,6 +514,11 @@ int stream_forward(const wt_problem* p, const float* c, const float* b, const fl
     WT_CUDA(cudaMemsetAsync(u2, 0, field * sizeof(float), st));
   }
   float* tape = reinterpret_cast<float*>(history);
+  if (!fields_out && tile_eligible(p) && vec4_ok(p, {u1, u2, history, workspace})) {
+    // large grid: K time steps per HBM round trip (wt_tile.cu)
+    float* extra = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + stream_ws_fwd_base(p));
+    return tile_forward(p, a1, a3, x, src_ij, prb_ij, prb_sq, u1, u2, probe_out, probe_raw, tape, extra, st, nullptr);
+  }
   const bool v4 = vec4_ok(p, {u1, u2, history, fields_out, workspace});
   const int vec = v4 ? 4 : 1;
   const int nbz = pick_batch_chunks(p, vec);
