@@ -183,6 +183,13 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 // =================================================================================================
 // adjoint
 // =================================================================================================
+// Written in the variable P_t = a3 * lambda_t.  Multiplying the adjoint recursion
+//     lambda_{t-1} = a1*lambda_t + L(a3*lambda_t) + (1-a1)*lambda_{t+1} + seed_{t-1}            (cell.py:39-42)
+// by a3 (all factors are own-cell) gives
+//     P_{t-1} = P_{t+1} + a1*(P_t - P_{t+1}) + a3*L(P_t) + a3*seed_{t-1},
+// i.e. exactly the forward update (wt_update) run backwards in time, with the probe seeds playing the role of the
+// sources.  So this kernel is the forward kernel plus the tape: sum_t L(u_{t-1})*P_t accumulates per cell and
+// dLoss/dc = gscale * sum / a3 = (2/c) * sum  (cell.py:36).  dLoss/dx[b,t] = sum over source pixels of P_t/a3.
 template <int R>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   const int NT = blockDim.x;
@@ -190,13 +197,13 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   const unsigned stage_bytes = (unsigned)(R * NT * sizeof(float4));
 
   extern __shared__ float4 smem4[];
-  float4* ring = smem4;                                        // [RING][R*NT]
-  float* fld = reinterpret_cast<float*>(ring + RING * R * NT);  // [2][slab]   P = a3*lambda
+  float4* ring = smem4;                                        // [RING][R*NT] tape stages
+  float* fld = reinterpret_cast<float*>(ring + RING * R * NT);  // [2][slab]   P
   float* ss = fld + 2 * slab_f;                                 // [2][TB][n_prb] probe seeds
   float* gxs = ss + 2 * TB * a.n_prb;                           // [2][TB]     dLoss/dx staging
   int* pown = reinterpret_cast<int*>(gxs + 2 * TB);             // [n_prb] owning thread, or -1
   int* pcell = pown + a.n_prb;                                  // [n_prb] cell index inside the owner's patch
-  uint64_t* full = reinterpret_cast<uint64_t*>(pcell + a.n_prb);  // [RING] tape stages; 8-byte aligned (even word count)
+  uint64_t* full = reinterpret_cast<uint64_t*>(pcell + a.n_prb);  // [RING]; 8-byte aligned (even word count before)
   uint64_t* bars = full + RING;                                 // [4] ghost rows
 
   Lane<R> L;
@@ -222,6 +229,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   bool has_probe = false;
   for (int p = 0; p < a.n_prb; ++p) has_probe |= (pown[p] == tid);
   const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
+  const size_t tape_step = (size_t)a.C * R * NT;
 
   float G[R][4];
 #pragma unroll
@@ -231,13 +239,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
 
   unsigned it_global = 0;   // tape stages consumed so far (ring slot / parity bookkeeping across samples)
   for (int b = L.cid; b < a.B; b += a.n_clusters) {
-    float lam[R][4], c2[R][4];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { lam[r][k] = 0.f; c2[r][k] = 0.f; }
-
-    auto tape_ptr = [&](int t) { return a.tape + ((((size_t)b * a.T + t) * a.C + L.rank) * R) * NT; };
+    const float4* tape_b = a.tape + (((size_t)b * a.T) * a.C + L.rank) * R * NT;   // stage of step t at + t*tape_step
     auto stage_seeds = [&](int blk) {   // seeds of time block blk: dLoss/d(raw probe value)
       const int t0 = blk * TB, n = min(TB, a.T - t0);
       float* dst = ss + (blk & 1) * TB * a.n_prb;
@@ -258,44 +260,65 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
         if (s != 0.f) atomicAdd(a.grad_x + (size_t)b * a.T + t0 + i, s);
       }
     };
+    // P += a3 * seed_t at the probe cells of my patch
+    auto add_seeds = [&](float (&P)[R][4], int t) {
+      if (has_probe) {
+        for (int p = 0; p < a.n_prb; ++p)
+          if (pown[p] == tid) {
+            const float sv = ss[((t / TB) & 1) * TB * a.n_prb + (t % TB) * a.n_prb + p];
+            const int pc = pcell[p];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (pc == r * 4 + k) P[r][k] = fmaf(k3[r][k], sv, P[r][k]);
+          }
+      }
+    };
     if (tid == 0) {   // prime the tape ring
       for (int s = 0; s < RING && s < a.T; ++s) {
         unsigned slot = (it_global + s) % RING;
         mbar_expect_tx(full + slot, stage_bytes);
-        bulk_g2s(ring + slot * R * NT, tape_ptr(a.T - 1 - s), stage_bytes, full + slot);
+        bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(a.T - 1 - s) * tape_step, stage_bytes, full + slot);
       }
     }
-    stage_seeds((a.T - 1) / TB);
+    const int last_blk = (a.T - 1) / TB;
+    stage_seeds(last_blk);
+    if (last_blk > 0) stage_seeds(last_blk - 1);
     __syncthreads();
 
-    for (int t = a.T - 1, it = 0; t >= 0; --t, ++it) {
+    float v[R][4], w[R][4];   // v = P_t, w = P_{t+1}
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[r][k] = 0.f; w[r][k] = 0.f; }
+    if (L.active) {
+      add_seeds(v, a.T - 1);
+      L.publish(a, fld, 0, v);
+    }
+    ++L.npub;
+    __syncthreads();
+
+    // One reverse step: `cu` = P_t (kept), `pr` = P_{t+1} on entry and P_{t-1} on exit.
+    auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int t, int it) {
+      const float* cur = fld + (it & 1) * L.slab;
       const int blk = t / TB, tt = t - blk * TB;
-      float* cur = fld + (it & 1) * L.slab;
-      if ((t == a.T - 1 || tt == TB - 1) && blk > 0) stage_seeds(blk - 1);
-      if (a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
+      // staging bookkeeping, once per block of TB steps: seeds two blocks ahead, dLoss/dx of the block just finished
+      if (tt == TB - 1 && t != a.T - 1) {
+        if (blk > 0) stage_seeds(blk - 1);
+        if (a.grad_x) flush_gx(blk + 1);
+      }
       const unsigned slot = (it_global + it) % RING, parity = ((it_global + it) / RING) & 1u;
-      float pv[R][4];
+      L.acquire_ghosts();
       if (L.active) {
-        if (has_probe) {   // lambda_t += dLoss/du_t through the probes
-          for (int p = 0; p < a.n_prb; ++p)
-            if (pown[p] == tid) {
-              const float sv = ss[(blk & 1) * TB * a.n_prb + tt * a.n_prb + p];
-              const int pc = pcell[p];
-#pragma unroll
-              for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (pc == r * 4 + k) lam[r][k] += sv;
-            }
-        }
-        if (a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t
+        if (a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
           float s = 0.f;
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (m1 >> (r * 4 + k) & 1u) s += lam[r][k];
-              if (m2 >> (r * 4 + k) & 1u) s += lam[r][k];
+              if (m1 >> (r * 4 + k) & 1u) s += cu[r][k] / k3[r][k];
+              if (m2 >> (r * 4 + k) & 1u) s += cu[r][k] / k3[r][k];
             }
           atomicAdd(gxs + (blk & 1) * TB + tt, s);
         }
@@ -303,41 +326,41 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const float4 l = ring[slot * R * NT + r * NT + tid];
-          const float lv[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            G[r][k] = fmaf(lv[k], lam[r][k], G[r][k]);     // cell.py:36, scaled once at the end
-            pv[r][k] = k3[r][k] * lam[r][k];
-          }
+          G[r][0] = fmaf(l.x, cu[r][0], G[r][0]);     // cell.py:36 up to the factor 2/c applied at the end
+          G[r][1] = fmaf(l.y, cu[r][1], G[r][1]);
+          G[r][2] = fmaf(l.z, cu[r][2], G[r][2]);
+          G[r][3] = fmaf(l.w, cu[r][3], G[r][3]);
         }
-        L.publish(a, fld, it & 1, pv);
+        if (t > 0) {
+          float lap[R][4];
+          patch_laplacian<R>(a.pitch, cur + own, cu, lap);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
+          add_seeds(pr, t - 1);
+          L.publish(a, fld, (it + 1) & 1, pr);
+        }
       }
-      ++L.npub;
+      if (t > 0) ++L.npub;
       __syncthreads();
       if (tid == 0 && it + RING < a.T) {   // every thread has read this slot: refill it RING steps ahead
         mbar_expect_tx(full + slot, stage_bytes);
-        bulk_g2s(ring + slot * R * NT, tape_ptr(t - RING), stage_bytes, full + slot);
+        bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(t - RING) * tape_step, stage_bytes, full + slot);
       }
-      L.acquire_ghosts();
-      if (L.active) {
-        float lapP[R][4];
-        patch_laplacian<R>(a.pitch, cur + own, pv, lapP);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float nl = c2[r][k] + fmaf(k1[r][k], lam[r][k], lapP[r][k]);   // cell.py:39-40
-            c2[r][k] = (1.f - k1[r][k]) * lam[r][k];                        // cell.py:42
-            lam[r][k] = nl;
-          }
-      }
+    };
+    int t = a.T - 1, it = 0;
+    for (; t >= 1; t -= 2, it += 2) {
+      step(v, w, t, it);
+      step(w, v, t - 1, it + 1);
     }
+    if (t == 0) step(v, w, 0, it);
     it_global += (unsigned)a.T;
     __syncthreads();
     if (a.grad_x) flush_gx(0);
     __syncthreads();
   }
-  // per-cluster partial of sum_{b,t} L(u_{t-1})*lambda_t ; reduced and scaled by k_finish_grad
+  // per-cluster partial of sum_{b,t} L(u_{t-1})*P_t ; reduced and scaled by 2/c in k_finish_grad_p
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -346,6 +369,15 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       if (L.active && gi < a.Nx && j < a.Ny) a.Gpart[((size_t)L.cid * a.Nx + gi) * a.Ny + j] = G[r][k];
     }
   if (a.C > 1) cg::this_cluster().sync();
+}
+
+__global__ void k_finish_grad_p(const float* __restrict__ G, const float* __restrict__ c, int n_part, size_t stride,
+                                size_t plane, float* __restrict__ grad_c) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  float s = 0.f;
+  for (int k = 0; k < n_part; ++k) s += G[(size_t)k * stride + i];
+  grad_c[i] = 2.f * s / c[i];
 }
 
 // =================================================================================================
@@ -618,7 +650,7 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
     return WT_OK;
   }
   WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st)));
-  k_finish_grad<<<fg, 256, 0, st>>>(Gpart, gs, plan.n_clusters, plane, plane, grad_c);
+  k_finish_grad_p<<<fg, 256, 0, st>>>(Gpart, c, plan.n_clusters, plane, plane, grad_c);
   if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
   if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));
   WT_CUDA(cudaGetLastError());

@@ -253,7 +253,7 @@ static TileGeom tile_geom(const wt_problem* p) {
   // extended tile: EH = runs*R rows, EW = 4*P4 columns with runs*P4 <= threads
   t.P4 = 32;                                   // 128 extended columns -> 128 - 2K owned
   t.EW = 4 * t.P4;
-  t.runs = (t.R == 4 ? 384 : 512) / t.P4;      // 12 or 16 row runs
+  t.runs = (t.R <= 2 ? 512 : 384) / t.P4;      // 16 or 12 row runs (launch bounds of k_tile_fwd)
   t.EH = t.runs * t.R;
   t.TH = t.EH - 2 * t.K;
   t.TW = t.EW - 2 * t.K;
