@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="waveforms per GPU")
     ap.add_argument("--T", type=int, default=T_STEPS)
+    ap.add_argument("--workload", default="vowel64", choices=["vowel64", "large"],
+                    help="vowel64 = BASELINE config 3 (the headline); large = config 5 window (4096^2, domain-decomposed for N>1)")
+    ap.add_argument("--grid", type=int, default=4096, help="large workload: grid edge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-T", type=int, default=0, help="time steps of the bounded CPU sample (0 = auto)")
     return ap.parse_args()
@@ -351,10 +354,104 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_large(args):
+    """BASELINE config 5 window: 4096x4096 grid, batch 8, T-step window, fwd + adjoint with checkpoints every 16 steps;
+    N > 1: ONE simulation split by rows over the GPUs (halo exchange every 16 steps), strong scaling."""
+    import math
+    import torch
+    import torch.distributed as dist
+    import wavetorch_b200 as wt
+    from wavetorch_b200 import _lib
+    from wavetorch_b200.domain import DomainDecomposedWaveRNN
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N, B, T, S = args.grid, (args.batch if args.batch != BATCH else 8), (args.T if args.T != T_STEPS else 64), 16
+    ii = torch.arange(N, dtype=torch.float32)[:, None]
+    jj = torch.arange(N, dtype=torch.float32)[None, :]
+    rho = 0.5 + 0.5 * torch.sin(2 * math.pi * ii / 97) * torch.cos(2 * math.pi * jj / 61)
+    geom = wt.WaveGeometryFreeForm((N, N), 1.4283556979968262, 1.0, 0.5, abs_N=20, abs_sig=3.0, abs_p=4.0, rho=rho)
+    probes = [wt.WaveIntensityProbe(N - 60, N // 2 + 20 * k) for k in (-1, 0, 1)]
+    model = wt.WaveRNN(wt.WaveCell(1.0, geom), [wt.WaveSource(60, N // 2)], probes).to(dev)
+    model.checkpoint_every = S
+    runner = DomainDecomposedWaveRNN(model, halo=S) if world > 1 else model
+    torch.manual_seed(0)
+    x = (0.1 * torch.randn(B, T)).to(dev)
+    w = torch.randn(B, T, 3).to(dev)
+    cells = B * T * N * N
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / steps
+
+    def train():
+        out = runner(x)
+        (out * w).sum().backward()
+        model.zero_grad(set_to_none=True)
+
+    def fwd():
+        with torch.no_grad():
+            runner(x)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        train()
+    l0 = _lib.launch_count
+    ms = timed(train, args.steps)
+    launches = _lib.launch_count - l0
+    fwd()
+    ms_f = timed(fwd, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        # unfused algorithmic bytes (SURVEY 8d): fwd 12 B, recompute with tape 16 B, adjoint 16 B per cell update
+        line = {"metric": METRIC, "value": cells / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "large", "source": "BASELINE config 5 window", "grid": [N, N], "global_batch": B,
+                           "time_steps": T, "checkpoint_every": S,
+                           "parallelism": ("row-slab domain decomposition x%d, halo %d" % (world, S)) if world > 1 else "1 GPU",
+                           "l2": "fields are %.1f GiB per time level (>> 126 MB L2)" % (B * N * N * 4 / 2 ** 30)},
+                "clocks": clocks, "gpu_launches": launches,
+                "fwd": {"value": cells / (ms_f * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_f},
+                "roofline": {"bound": "hbm", "kernel": "k_tile_fwd (forward only)", "achieved": 12.0 * cells / (ms_f * 1e-3) / 1e9 / world,
+                             "peak": peak, "unit": "GB/s", "frac": 12.0 * cells / (ms_f * 1e-3) / 1e9 / world / peak,
+                             "peak_source": peak_src, "algorithmic_bytes_per_cell_update": 12.0, "traffic": None,
+                             "note": "per GPU; temporal blocking moves fewer bytes than the 12 B/update of an unblocked sweep"},
+                "e2e": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "large":
+        run_large(args)
     else:
         run_ours(args)
 
