@@ -513,7 +513,8 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
       const double lane = (double)nact / threads;
       const double sync_cost = C > 1 ? 0.85 : 1.0;
       const double par = threads >= 384 ? 1.0 : threads / 384.0;
-      const double regs = (!nl && R >= 6) ? 0.8 : 1.0;   // measured: R = 4..5 beats 6..8 (register pressure in the adjoint)
+      // measured: linear R = 4..5 beats 6..8; the nonlinear adjoint keeps ~10 values per cell live and is fastest at R = 1
+      const double regs = nl ? (R == 1 ? 1.6 : R == 2 ? 1.0 : 0.6) : (R >= 6 ? 0.8 : 1.0);
       const double score = (rim * lane * sync_cost * par * regs) / ((double)waves * Hc * per_sm);
       if (score > best_score) { best_score = score; bestC = C; bestR = R; }
     }
