@@ -253,21 +253,46 @@ def run_ours(args):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         train_step(x_dev, labels)
-    l0 = _lib.launch_count
-    t_wall = time.perf_counter()
-    ms_step = timed(lambda: train_step(x_dev, labels), args.steps)
-    t_wall = time.perf_counter() - t_wall
-    launches = _lib.launch_count - l0
 
-    # end to end: inputs come from pinned host memory, the loss goes back to the host, every step
-    def e2e_step():
+    # The iteration is replayed from a CUDA graph (wavetorch_b200.graph.GraphedTrainStep, part of the public API):
+    # same kernels, no host launch latency between them.  If capture is not possible the eager loop is timed.
+    graphed, mode = None, "eager"
+    if os.environ.get("WT_BENCH_EAGER", "0") != "1":
+        try:
+            from wavetorch_b200.graph import GraphedTrainStep
+            opt_g = torch.optim.Adam(model.parameters(), lr=4e-4, capturable=True)
+            graphed = GraphedTrainStep(
+                runner, opt_g, lambda out, y: torch.nn.functional.cross_entropy(wt.utils.normalize_power(out.sum(dim=1)), y),
+                x_dev, labels, warmup=max(args.warmup, 3))
+            graphed(x_dev, labels)
+            mode = "cuda-graph"
+        except Exception as exc:  # pragma: no cover
+            graphed = None
+            sys.stderr.write("bench: CUDA-graph capture failed (%r); timing the eager loop\n" % (exc,))
+
+    def step_resident():
+        return graphed(x_dev, labels) if graphed is not None else train_step(x_dev, labels)
+
+    def step_e2e():      # inputs from pinned host memory, loss back to the host, every step
+        if graphed is not None:
+            return graphed(x_host, labels_host).item()
         xb = x_host.to(dev, non_blocking=True)
         yb = labels_host.to(dev, non_blocking=True)
         return train_step(xb, yb).item()
 
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    l0 = _lib.launch_count
+    n_launch_eager = None
+    t_wall = time.perf_counter()
+    ms_step = timed(step_resident, args.steps, warm=1)
+    t_wall = time.perf_counter() - t_wall
+    launches = _lib.launch_count - l0
+    ms_e2e = timed(step_e2e, args.steps, warm=2)
+    # the eager loop, for reference (and to count the launches one iteration makes)
+    l0 = _lib.launch_count
+    ms_eager = timed(lambda: train_step(x_dev, labels), args.steps, warm=1)
+    launches_eager = (_lib.launch_count - l0) // (args.steps + 1) * args.steps
+    if graphed is not None:
+        launches = launches_eager      # a replay launches the same kernels as the iteration it captured
 
     # forward only (inference, no tape)
     def fwd_only():
@@ -301,10 +326,22 @@ def run_ours(args):
     ms_bwd = statistics.median(bw_ms)
     clocks = sampler.stop() if rank == 0 else None
 
-    if rank != 0:
+    def teardown():
+        # Drop the captured graph (it holds NCCL work when world > 1) before leaving; with graphs alive
+        # destroy_process_group() was seen to hang, so multi-rank runs synchronise and exit without it.
+        nonlocal graphed
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        teardown()
         return
 
     peak, peak_src = peak_hbm()
@@ -322,7 +359,10 @@ def run_ours(args):
         "data": "synthetic", "config": config_dict(args, world), "clocks": clocks,
         "e2e": {"value": world * cells_per_step / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + labels_host.numel() * 8), "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e},
+                "ms_per_step": ms_e2e, "mode": mode},
+        "eager": {"value": world * cells_per_step / (ms_eager * 1e-3) / 1e9, "ms_per_step": ms_eager,
+                  "what": "same iteration launched from Python without graph capture, inputs resident"},
+        "mode": mode,
         "gpu_launches": launches,
         "fwd": {"value": world * cells_per_step / (ms_fwd * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_fwd,
                 "what": "forward only (torch.no_grad, no tape), same workload"},
@@ -349,9 +389,7 @@ def run_ours(args):
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    teardown()
 
 
 def run_large(args):

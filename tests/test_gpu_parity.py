@@ -467,3 +467,27 @@ def test_temporally_blocked_forward_matches_per_step_kernels(shape, T, K, R, mon
     (out * w).sum().backward()
     assert torch.equal(out, out_ref)          # same arithmetic, same association order: bitwise equal
     assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), ref.cell.geom.rho.grad.cpu().numpy()) < 1e-6
+
+
+def test_cuda_graph_training_step_matches_eager():
+    """GraphedTrainStep (one captured iteration of train.py:59-72) replays to the same parameters as the eager loop."""
+    from wavetorch_b200.graph import GraphedTrainStep
+    B, T = 6, 300
+    x = torch.tensor(wo.synthetic_vowels(B, T), device=DEV)
+    y = torch.arange(B, device=DEV) % 3
+    loss_fn = lambda out, lab: torch.nn.functional.cross_entropy(wt.utils.normalize_power(out.sum(dim=1)), lab)
+    m1, m2 = _vowel_model(), _vowel_model()
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-3, capturable=True)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3, capturable=True)
+    losses1 = []
+    for _ in range(4):      # 3 warm-up iterations inside GraphedTrainStep + 1 replay below = 4 eager iterations
+        o1.zero_grad(set_to_none=True)
+        l = loss_fn(m1(x), y); l.backward(); o1.step(); m1.cell.geom.constrain_to_design_region()
+        losses1.append(l.item())
+    g = GraphedTrainStep(m2, o2, loss_fn, x, y, warmup=3)
+    # capture itself does not execute; the first replay is iteration number 4
+    l2 = g(x, y).item()
+    assert abs(l2 - losses1[3]) < 1e-6
+    assert rel_l2(m2.cell.geom.rho.detach().cpu().numpy(), m1.cell.geom.rho.detach().cpu().numpy()) < 1e-6
+    l3 = g(x.cpu().pin_memory(), y.cpu().pin_memory()).item()     # host-pinned inputs
+    assert l3 < l2 + 1e-3

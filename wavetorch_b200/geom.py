@@ -191,10 +191,13 @@ class WaveGeometryFreeForm(WaveGeometry):
             raise ValueError('The domain initialization is invalid')
 
     def constrain_to_design_region(self):
-        """Zero rho outside the design region and inside the absorber (geom.py:201-205)."""
+        """Zero rho outside the design region and inside the absorber (geom.py:201-205).
+
+        Written as a masked select instead of boolean-mask assignment: same result, but no host synchronisation (the
+        mask assignment has to count its True entries on the host) and therefore capturable in a CUDA graph."""
         with torch.no_grad():
-            self.rho[self.design_region == 0] = 0.0
-            self.rho[self.b > 0] = 0.0
+            keep = (self.design_region != 0) & ~(self.b > 0)
+            self.rho.copy_(torch.where(keep, self.rho, torch.zeros_like(self.rho)))
 
     def _apply_blur(self, rho):
         """blur_N passes of the zero-padded disk stencil (geom.py:207-215).
