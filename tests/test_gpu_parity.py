@@ -491,3 +491,57 @@ def test_cuda_graph_training_step_matches_eager():
     assert rel_l2(m2.cell.geom.rho.detach().cpu().numpy(), m1.cell.geom.rho.detach().cpu().numpy()) < 1e-6
     l3 = g(x.cpu().pin_memory(), y.cpu().pin_memory()).item()     # host-pinned inputs
     assert l3 < l2 + 1e-3
+
+
+def test_holey_geometry_end_to_end():
+    """WaveGeometryHoley (geom.py:88-132): gradients w.r.t. hole positions/radii flow from the CUDA adjoint through the
+    PyTorch parameterisation; checked against the float64 oracle adjoint chained through the same parameterisation."""
+    Nx, Ny, N, B, T = 44, 40, 5, 2, 70
+    kw = dict(abs_N=N, abs_sig=4.0, abs_p=3.0, eta=0.5, beta=20.0, x=[14.3, 27.6], y=[12.2, 24.7], r=[3.0, 4.5])
+    gh = wt.WaveGeometryHoley((Nx, Ny), 1.0, 1.0, 0.5, **kw)
+    m = wt.WaveRNN(wt.WaveCell(0.6, gh), [wt.WaveSource(8, 20)], [wt.WaveIntensityProbe(35, 14), wt.WaveProbe(34, 27)]).to(DEV)
+    rng = np.random.RandomState(2)
+    x0 = (0.4 * rng.randn(B, T)).astype(np.float32)
+    w0 = rng.randn(B, T, 2)
+    out = m(torch.tensor(x0, device=DEV))
+    (out * torch.tensor(w0, dtype=torch.float32, device=DEV)).sum().backward()
+    # float64 chain on the CPU: c from the same module in float64, dLoss/dc from the oracle adjoint
+    wt.utils.set_dtype("float64")
+    try:
+        g64 = wt.WaveGeometryHoley((Nx, Ny), 1.0, 1.0, 0.5, **kw)
+        c = g64.c
+        b = wo.pml_damping(Nx, Ny, N, 4.0, 3.0, np.float64)
+        src, prb, sq = np.array([[8, 20]]), np.array([[35, 14], [34, 27]]), np.array([True, False])
+        f = wo.forward(c.detach().numpy(), b, None, x0.astype(np.float64), src, prb, np.float64(np.float32(0.6)), 1.0, keep_fields=True)
+        a = wo.adjoint(c.detach().numpy(), b, None, x0.astype(np.float64), src, prb, sq, np.float64(np.float32(0.6)), 1.0, w0, f)
+        c.backward(torch.tensor(a["grad_c"]))
+    finally:
+        wt.utils.set_dtype("float32")
+    assert rel_l2(out.detach().cpu().numpy(), wo.probe_outputs(f["raw"], sq)) < 1e-5
+    for name in ("x", "y", "r"):
+        got, ref = getattr(gh, name).grad.cpu().numpy(), getattr(g64, name).grad.numpy()
+        assert rel_l2(got, ref) < 2e-4, (name, got, ref)
+    assert m.cell.geom.rho.shape == (Nx, Ny)          # Holey.rho is the projected field (geom.py:126-128)
+
+
+def test_multi_pixel_probes_and_batched_line_source():
+    """Multi-pixel probes return [B,T,n,P] like the reference's stack of [B,n] readouts (SURVEY B-3b); a line source
+    with B > 1 feeds every pixel of the line with x[b,t] (documented divergence from source.py:20, SURVEY B-2)."""
+    Nx, Ny, N, B, T = 40, 36, 4, 3, 40
+    geom = wt.WaveGeometryFreeForm((Nx, Ny), 1.0, 1.0, 0.6, abs_N=N, abs_sig=3.0, abs_p=3.0, beta=10.0, rho="half")
+    line = wt.WaveLineSource(8, 10, 8, 20)
+    pa = wt.WaveProbe([30, 30, 31], [10, 18, 25])
+    pb = wt.WaveIntensityProbe([28, 29, 30], [12, 20, 30])
+    m = wt.WaveRNN(wt.WaveCell(0.6, geom), [line], [pa, pb]).to(DEV)
+    x0 = (0.3 * np.random.RandomState(4).randn(B, T)).astype(np.float32)
+    out = m(torch.tensor(x0, device=DEV))
+    assert out.shape == (B, T, 3, 2)
+    b = wo.pml_damping(Nx, Ny, N, 3.0, 3.0, np.float64)
+    rho = wo.constrain_to_design_region(np.full((Nx, Ny), 0.5), None, b)
+    c = wo.wave_speed(rho, 1.0, 0.6, 0.5, 10.0, 1, 1)
+    src = np.stack([np.full(11, 8), np.arange(10, 21)], axis=1)
+    prb = np.array([[30, 10], [30, 18], [31, 25], [28, 12], [29, 20], [30, 30]])
+    f = wo.forward(c, b, None, x0.astype(np.float64), src, prb, np.float64(np.float32(0.6)), 1.0)
+    ref = wo.probe_outputs(f["raw"], [False] * 3 + [True] * 3)
+    ref = np.stack([ref[:, :, :3], ref[:, :, 3:]], axis=-1)
+    assert rel_l2(out.detach().cpu().numpy(), ref) < 1e-5

@@ -83,13 +83,13 @@ __device__ __forceinline__ void wt_nl_bc(const Scalars& s, float bpml, float cli
   if (SAT) {
     float r = u1 * s.inv_uth;
     d = fmaf(r, r, 1.f);
-    b = fmaf(rho, s.b0 / d, bpml);
+    b = fmaf(rho * s.b0, __frcp_rn(d), bpml);   // correctly rounded reciprocal: a few instructions, no division routine
   }
   if (KERR) c = fmaf(rho * s.c_nl, u1 * u1, clin);
 }
 
 __device__ __forceinline__ CellCoef wt_coef(const Scalars& s, float b, float c) {
-  float q = 1.f / fmaf(b, s.dt, 1.f);
+  float q = __frcp_rn(fmaf(b, s.dt, 1.f));
   CellCoef k;
   k.a1 = 2.f * q;
   k.a3 = q * s.kappa * c * c;

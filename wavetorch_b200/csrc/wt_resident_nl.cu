@@ -13,7 +13,7 @@ namespace wt {
 
 template <int R>
 constexpr int res_nl_max_threads() {
-  return R <= 1 ? 1024 : R == 2 ? 640 : R == 3 ? 448 : 384;
+  return R <= 2 ? 512 : R == 3 ? 448 : 384;   // register budget: the nonlinear adjoint keeps ~9 values per cell live
 }
 
 template <int R>
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
       const unsigned gi = it_global + it;
       const unsigned slot = gi % RG, parity = (gi / RG) & 1u;
       const unsigned slot2 = (gi + 1) % RG, parity2 = ((gi + 1) / RG) & 1u;   // stage of step t-1: its u is my u_{t-2}
-      float pv[R][4], g1[R][4], g2[R][4];
+      float pv[R][4], g2[R][4];   // across the barrier: P (stencil centre), the new carry; lam holds c2 + own-cell part
       if (L.active) {
         if (has_probe) {
           for (int p = 0; p < a.n_prb; ++p)
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
             float bb, cc, d;
             wt_nl_bc<SAT, KERR>(s, bp[r][k], cl[r][k], rh[r][k], u1, bb, cc, d);
             const float beta = bb * s.dt;
-            const float q = 1.f / (1.f + beta);
+            const float q = __frcp_rn(1.f + beta);
             const float ql = q * lam[r][k];
             const float kl = s.kappa * lpa[k];
             const float S = fmaf(cc * cc, kl, 2.f * (u1 - u2));
@@ -343,8 +343,9 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
             float gu1 = 2.f * ql;                             // own-cell part of cell.py:39-40
             if (SAT) {
               const float iu = s.inv_uth;
-              Gr[r][k] = fmaf(g_b, s.b0 / d, Gr[r][k]);
-              gu1 = fmaf(g_b, rh[r][k] * s.b0 * (-2.f * u1 * iu * iu) / (d * d), gu1);
+              const float rd = __frcp_rn(d);
+              Gr[r][k] = fmaf(g_b, s.b0 * rd, Gr[r][k]);
+              gu1 = fmaf(g_b, rh[r][k] * s.b0 * (-2.f * u1 * iu * iu) * (rd * rd), gu1);
             }
             if (KERR) {
               Gr[r][k] = fmaf(g_c, s.c_nl * u1 * u1, Gr[r][k]);
@@ -352,8 +353,8 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
             }
             Gc[r][k] += g_c;
             pv[r][k] = s.kappa * cc * cc * ql;
-            g1[r][k] = gu1;
             g2[r][k] = (beta - 1.f) * ql;                     // cell.py:42
+            lam[r][k] = c2[r][k] + gu1;                       // everything of lambda_{t-1} except the stencil term
           }
         }
         L.publish(a, fld, it & 1, pv);
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            lam[r][k] = c2[r][k] + (g1[r][k] + lapP[r][k]);
+            lam[r][k] += lapP[r][k];
             c2[r][k] = g2[r][k];
           }
       }
@@ -402,8 +403,8 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
 // =================================================================================================
 int res_nl_max_threads_rt(int R) {
   switch (R) {
-    case 1: return 1024;
-    case 2: return 640;
+    case 1: return 512;
+    case 2: return 512;
     case 3: return 448;
     case 4: return 384;
     default: return 0;

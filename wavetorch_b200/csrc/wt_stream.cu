@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(128) k_stream_adjA(AdjNlArgs a) {
     float bb, cc, d;
     wt_nl_bc<SAT, KERR>(a.s, bp, cl, rh, u1, bb, cc, d);
     const float beta = bb * a.s.dt;
-    const float q = 1.f / (1.f + beta);
+    const float q = __frcp_rn(1.f + beta);
     const float ql = q * lam;
     const float kl = a.s.kappa * lap;
     const float S = fmaf(cc * cc, kl, 2.f * (u1 - u2));
@@ -332,8 +332,9 @@ __global__ void __launch_bounds__(128) k_stream_adjA(AdjNlArgs a) {
     float gu1 = 2.f * ql;                             // own-cell part of cell.py:39-40
     if (SAT) {
       const float iu = a.s.inv_uth;
-      gr = fmaf(g_b, a.s.b0 / d, gr);
-      gu1 = fmaf(g_b, rh * a.s.b0 * (-2.f * u1 * iu * iu) / (d * d), gu1);
+      const float rd = __frcp_rn(d);
+      gr = fmaf(g_b, a.s.b0 * rd, gr);
+      gu1 = fmaf(g_b, rh * a.s.b0 * (-2.f * u1 * iu * iu) * (rd * rd), gu1);
     }
     if (KERR) {
       gr = fmaf(g_c, a.s.c_nl * u1 * u1, gr);
