@@ -15,6 +15,7 @@
 // Reference semantics: wavetorch/rnn.py:36-70, cell.py:12-17, cell.py:27-44, operators.py:5-11,
 // source.py:15-22, probe.py:14-27.
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "wt_resident.h"
@@ -26,7 +27,7 @@ namespace wt {
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int R>
+template <int R, bool TAPE>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
   const int slab_f = (a.Hc + 2) * a.pitch;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
     for (int i = tid; i < TB && i < a.T; i += NT) xs[i] = xb[i];
     __syncthreads();
 
-    float4* tape = a.tape ? a.tape + (((size_t)b * a.T) * a.C + L.rank) * R * NT + tid : nullptr;
+    float4* tape = TAPE ? a.tape + (((size_t)b * a.T) * a.C + L.rank) * R * NT + tid : nullptr;
     float* fout = a.fields ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
 
     auto flush = [&](int blk) {   // probe samples of time block blk -> HBM
@@ -89,19 +90,25 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
       }
     };
     // One time step: `cu` = u_t (kept), `pr` = u_{t-1} on entry and u_{t+1} on exit.  t is the index of the new field.
-    auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int t, int blk, int tt) {
-      const float* cur = fld + (t & 1) * L.slab;
+    // PAR = t & 1 is a compile-time constant of each of the two unrolled copies, so every shared-memory address below
+    // is loop invariant.  x and the probe samples live in rings of 2*TB steps.
+    const float* rd0 = fld + own;                 // my patch in slab buffer 0 / 1
+    const float* rd1 = fld + L.slab + own;
+    float* psw = ps + tid;                        // probe ring slot of this lane (lanes < n_prb only)
+    auto step = [&](auto par, float (&cu)[R][4], float (&pr)[R][4], int t) {
+      constexpr int PAR = decltype(par)::value;
+      const float* cur = PAR ? rd1 : rd0;
       L.acquire_ghosts();
-      if (t > 0 && my_poff >= 0) ps[(((t - 1) / TB) & 1) * TB * a.n_prb + ((t - 1) % TB) * a.n_prb + tid] = cur[my_poff];
+      if (my_poff >= 0 && t > 0) psw[((t - 1) & (2 * TB - 1)) * a.n_prb] = (PAR ? fld + L.slab : fld)[my_poff];
       if (L.active) {
         float lap[R][4];
-        patch_laplacian<R>(a.pitch, cur + own, cu, lap);
+        patch_laplacian<R>(a.pitch, cur, cu, lap);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         if (m1) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t]
-          const float xv = xs[(blk & 1) * TB + tt];
+          const float xv = xs[t & (2 * TB - 1)];
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -110,8 +117,8 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
               if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
             }
         }
-        L.publish(a, fld, (t + 1) & 1, pr);
-        if (tape) {
+        L.publish(a, fld, PAR ^ 1, pr);
+        if (TAPE) {
 #pragma unroll
           for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
           tape += tape_step;
@@ -136,6 +143,8 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
       ++L.npub;
       __syncthreads();
     };
+    using P0 = std::integral_constant<int, 0>;
+    using P1 = std::integral_constant<int, 1>;
 
     const int nblk = (a.T + TB - 1) / TB;
     for (int blk = 0; blk < nblk; ++blk) {
@@ -148,11 +157,11 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
       if (blk >= 2) flush(blk - 2);
       int tt = 0;
       for (; tt + 1 < n; tt += 2) {     // two steps per iteration: the two time levels swap roles, no moves
-        step(v, w, t0 + tt, blk, tt);
-        step(w, v, t0 + tt + 1, blk, tt + 1);
+        step(P0{}, v, w, t0 + tt);
+        step(P1{}, w, v, t0 + tt + 1);
       }
       if (tt < n) {                      // odd tail (last block only): keep "v = latest" by swapping once
-        step(v, w, t0 + tt, blk, tt);
+        step(P0{}, v, w, t0 + tt);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -299,16 +308,23 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     ++L.npub;
     __syncthreads();
 
-    // One reverse step: `cu` = P_t (kept), `pr` = P_{t+1} on entry and P_{t-1} on exit.
-    auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int t, int it) {
-      const float* cur = fld + (it & 1) * L.slab;
-      const int blk = t / TB, tt = t - blk * TB;
+    // One reverse step: `cu` = P_t (kept), `pr` = P_{t+1} on entry and P_{t-1} on exit.  PAR = it & 1 is a compile-time
+    // constant of each of the two unrolled copies (shared-memory addresses are loop invariant).
+    const float* rd0 = fld + own;
+    const float* rd1 = fld + L.slab + own;
+    const float4* ring_me = ring + tid;
+    auto step = [&](auto par, float (&cu)[R][4], float (&pr)[R][4], int t, int it) {
+      constexpr int PAR = decltype(par)::value;
+      const float* cur = PAR ? rd1 : rd0;
+      const int tt = t & (TB - 1);
       // staging bookkeeping, once per block of TB steps: seeds two blocks ahead, dLoss/dx of the block just finished
       if (tt == TB - 1 && t != a.T - 1) {
+        const int blk = t / TB;
         if (blk > 0) stage_seeds(blk - 1);
         if (a.grad_x) flush_gx(blk + 1);
       }
-      const unsigned slot = (it_global + it) % RING, parity = ((it_global + it) / RING) & 1u;
+      const unsigned gi = it_global + it;
+      const unsigned slot = gi & (RING - 1), parity = (gi / RING) & 1u;
       L.acquire_ghosts();
       if (L.active) {
         if (a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
@@ -320,12 +336,13 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
               if (m1 >> (r * 4 + k) & 1u) s += cu[r][k] / k3[r][k];
               if (m2 >> (r * 4 + k) & 1u) s += cu[r][k] / k3[r][k];
             }
-          atomicAdd(gxs + (blk & 1) * TB + tt, s);
+          atomicAdd(gxs + (t & (2 * TB - 1)), s);
         }
         mbar_wait(full + slot, parity);
+        const float4* rs = ring_me + slot * R * NT;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const float4 l = ring[slot * R * NT + r * NT + tid];
+          const float4 l = rs[r * NT];
           G[r][0] = fmaf(l.x, cu[r][0], G[r][0]);     // cell.py:36 up to the factor 2/c applied at the end
           G[r][1] = fmaf(l.y, cu[r][1], G[r][1]);
           G[r][2] = fmaf(l.z, cu[r][2], G[r][2]);
@@ -333,13 +350,13 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
         }
         if (t > 0) {
           float lap[R][4];
-          patch_laplacian<R>(a.pitch, cur + own, cu, lap);
+          patch_laplacian<R>(a.pitch, cur, cu, lap);
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
           add_seeds(pr, t - 1);
-          L.publish(a, fld, (it + 1) & 1, pr);
+          L.publish(a, fld, PAR ^ 1, pr);
         }
       }
       if (t > 0) ++L.npub;
@@ -349,12 +366,14 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
         bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(t - RING) * tape_step, stage_bytes, full + slot);
       }
     };
+    using P0 = std::integral_constant<int, 0>;
+    using P1 = std::integral_constant<int, 1>;
     int t = a.T - 1, it = 0;
     for (; t >= 1; t -= 2, it += 2) {
-      step(v, w, t, it);
-      step(w, v, t - 1, it + 1);
+      step(P0{}, v, w, t, it);
+      step(P1{}, w, v, t - 1, it + 1);
     }
-    if (t == 0) step(v, w, 0, it);
+    if (t == 0) step(P0{}, v, w, 0, it);
     it_global += (unsigned)a.T;
     __syncthreads();
     if (a.grad_x) flush_gx(0);
@@ -436,7 +455,7 @@ static int resident_clusters(int device, int R, int C, int threads, size_t smem_
     if (k.dev == device && k.R == R && k.C == C && k.threads == threads && k.sf == smem_fwd && k.sb == smem_bwd) return k.n;
   int nf = 0, nb = 0;
   switch (R) {
-#define WT_OCC(R_) case R_: nf = active_clusters(k_res_fwd<R_>, C, threads, smem_fwd); nb = active_clusters(k_res_adj<R_>, C, threads, smem_bwd); break;
+#define WT_OCC(R_) case R_: { int n0 = active_clusters(k_res_fwd<R_, false>, C, threads, smem_fwd); int n1 = active_clusters(k_res_fwd<R_, true>, C, threads, smem_fwd); nf = n0 < n1 ? n0 : n1; nb = active_clusters(k_res_adj<R_>, C, threads, smem_bwd); } break;
     WT_OCC(1) WT_OCC(2) WT_OCC(3) WT_OCC(4) WT_OCC(5) WT_OCC(6) WT_OCC(8)
 #undef WT_OCC
     default: break;
@@ -614,7 +633,8 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
   a.tape = reinterpret_cast<float4*>(history);
   a.status = status;
   if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st);
-  WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R>, plan, plan.smem_fwd, a, st)));
+  if (a.tape) { WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, true>, plan, plan.smem_fwd, a, st))); }
+  else { WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, false>, plan, plan.smem_fwd, a, st))); }
   return WT_OK;
 }
 

@@ -106,7 +106,8 @@ class _DomainLoop(torch.autograd.Function):
         if min(s.r1 - s.r0 for s in slabs) < halo:
             raise ValueError("domain decomposition: every rank needs at least `halo` (= %d) rows" % halo)
         need = ctx.needs_input_grad
-        want_grad = any(need[:4]) and T > 0
+        nonlinear = spec.b0 > 0 or spec.c_nl != 0
+        want_grad = spec.track_grad and T > 0 and (need[0] or need[1] or need[2] or (need[3] and nonlinear))
         segs = [(s0, min(s0 + halo, T)) for s0 in range(0, T, halo)]
         loc = []   # per slab: local coefficient slices and state
         for s in slabs:
@@ -143,6 +144,8 @@ class _DomainLoop(torch.autograd.Function):
             dist.all_reduce(out, group=group)
             if want_grad:
                 dist.all_reduce(raw, group=group)
+        ctx.no_tape = not want_grad
+        ctx.shape = (Nx, Ny)
         if want_grad:
             ctx.meta = (spec, halo, group, virtual, slabs, loc, segs, raw, x32, Nx,
                         (x.dtype, c.dtype, b.dtype, rho.dtype if rho is not None else None))
@@ -150,6 +153,10 @@ class _DomainLoop(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.no_tape:
+            need = ctx.needs_input_grad
+            zero = torch.zeros(ctx.shape, device=grad_out.device, dtype=grad_out.dtype) if need[3] else None
+            return None, None, None, zero, None, None, None, None
         lib = _lib.load()
         spec, halo, group, virtual, slabs, loc, segs, raw, x32, NX, dtypes = ctx.meta
         dev = x32.device
@@ -245,5 +252,5 @@ class DomainDecomposedWaveRNN(torch.nn.Module):
         if getattr(geom, "_h_host", None) is None:
             geom._h_host = float(geom.h)
         spec = LoopSpec(src_ij=tab["src_ij"], prb_ij=tab["prb_ij"], prb_sq=tab["prb_sq"], dt=s["dt"], h=geom._h_host,
-                        b0=s["b0"], uth=s["uth"], c_nl=s["c_nl"])
+                        b0=s["b0"], uth=s["uth"], c_nl=s["c_nl"], track_grad=torch.is_grad_enabled())
         return _DomainLoop.apply(x, c, b, rho, spec, self.halo, self.group, self.virtual_ranks)

@@ -49,6 +49,7 @@ class LoopSpec:
     rows_per_thread: int = 0
     checkpoint_every: int = 0   # > 0: keep only (u_t, u_{t-1}) every S steps and recompute each segment's tape in backward
     batch_chunk: int = 0        # > 0: process the batch in chunks of this many waveforms (bounds the tape / checkpoints)
+    track_grad: bool = True     # grad mode of the caller (Function.forward itself always runs with grad disabled)
 
 
 def _call_forward(lib, prob, dev, c32, b32, rho32, x32, spec, u1, u2, probe_out, probe_raw, fields, hist, ws):
@@ -99,7 +100,8 @@ class _CheckpointedLoop(torch.autograd.Function):
         Nx, Ny = c32.shape
         n_prb = spec.prb_ij.shape[0]
         need = ctx.needs_input_grad
-        want_grad = any(need[:4]) and T > 0
+        nonlinear = spec.b0 > 0 or spec.c_nl != 0
+        want_grad = spec.track_grad and T > 0 and (need[0] or need[1] or need[2] or (need[3] and nonlinear))
         segs = _CheckpointedLoop._segments(T, int(spec.checkpoint_every))
         bc = int(spec.batch_chunk) if spec.batch_chunk else B
         chunks = [(b0, min(b0 + bc, B)) for b0 in range(0, B, bc)]
@@ -120,6 +122,8 @@ class _CheckpointedLoop(torch.autograd.Function):
                               None, ws)
                 _lib.count_launches(plan.launches_fwd)
                 out[b0:b1, s0:s1] = po
+        ctx.no_tape = not want_grad
+        ctx.shape = (Nx, Ny)
         if want_grad:
             ctx.spec, ctx.segs, ctx.chunks, ctx.ckpts = spec, segs, chunks, ckpts
             ctx.saved = (x32, c32, b32, rho32)
@@ -128,6 +132,10 @@ class _CheckpointedLoop(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.no_tape:
+            need = ctx.needs_input_grad
+            zero = torch.zeros(ctx.shape, device=grad_out.device, dtype=grad_out.dtype) if need[3] else None
+            return None, None, None, zero, None
         lib = _lib.load()
         spec, segs, chunks, ckpts = ctx.spec, ctx.segs, ctx.chunks, ctx.ckpts
         x32, c32, b32, rho32 = ctx.saved
@@ -200,7 +208,9 @@ class _WaveLoop(torch.autograd.Function):
         B, T = x32.shape
         Nx, Ny = c32.shape
         need = ctx.needs_input_grad
-        want_grad = any(need[:4]) and T > 0
+        nonlinear = spec.b0 > 0 or spec.c_nl != 0
+        # rho enters the loop only through the nonlinear terms; without them (or with autograd off) no tape is written
+        want_grad = spec.track_grad and T > 0 and (need[0] or need[1] or need[2] or (need[3] and nonlinear))
         flags = spec.flags | _lib.WT_F_ZERO_INIT
         if need[2]:
             flags |= _lib.WT_F_NEED_GRAD_B
@@ -226,6 +236,8 @@ class _WaveLoop(torch.autograd.Function):
                                 _lib.stream_ptr(dev))
         _lib.check(st, "wt_forward")
         _lib.count_launches(plan.launches_fwd)
+        ctx.no_tape = not want_grad
+        ctx.shape = (Nx, Ny)
         if want_grad:
             ctx.prob, ctx.plan, ctx.spec = prob, plan, spec
             ctx.saved = (c32, b32, rho32, probe_raw, hist)
@@ -235,6 +247,10 @@ class _WaveLoop(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.no_tape:   # only reachable when rho requires grad in linear mode: it does not enter the loop
+            need = ctx.needs_input_grad
+            zero = torch.zeros(ctx.shape, device=grad_out.device, dtype=grad_out.dtype) if need[3] else None
+            return None, None, None, zero, None
         lib = _lib.load()
         prob, plan, spec = ctx.prob, ctx.plan, ctx.spec
         c32, b32, rho32, probe_raw, hist = ctx.saved
@@ -269,6 +285,7 @@ class _WaveLoop(torch.autograd.Function):
 
 def wave_rnn(x, c, b, rho, spec):
     """Run the fused time loop.  x [B,T]; c, b, rho [Nx,Ny]; returns [B,T,n_prb] (or [B,T,Nx,Ny])."""
+    spec.track_grad = torch.is_grad_enabled()
     if spec.checkpoint_every and spec.checkpoint_every > 0 and spec.checkpoint_every < x.shape[1]:
         return _CheckpointedLoop.apply(x, c, b, rho, spec)
     return _WaveLoop.apply(x, c, b, rho, spec)
