@@ -99,7 +99,6 @@ def make_problem(Nx, Ny, B, T, n_src, n_prb, dt, h, b0=0.0, uth=0.0, c_nl=0.0, f
     p.dt, p.h, p.b0, p.uth, p.c_nl = float(dt), float(h), float(b0), float(uth), float(c_nl)
     p.cluster = int(os.environ.get("WT_CLUSTER", cluster))
     p.rows_per_thread = int(os.environ.get("WT_ROWS", rows_per_thread))
-    p.reserved[0] = int(os.environ.get("WT_TUNE", 0))
     return p
 
 

@@ -235,10 +235,16 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
-  bool has_probe = false;
-  for (int p = 0; p < a.n_prb; ++p) has_probe |= (pown[p] == tid);
+  int pc0 = -1, pi0 = 0;       // first probe inside my patch: cell index and probe index
+  bool more_probes = false;
+  for (int p = 0; p < a.n_prb; ++p)
+    if (pown[p] == tid) {
+      if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
+    }
   const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
   const size_t tape_step = (size_t)a.C * R * NT;
+  // the lane that re-issues tape copies sits in a middle warp: the first and last warps already wait for ghost rows
+  const int refill_tid = ((NT / 32) / 2) * 32;
 
   float G[R][4];
 #pragma unroll
@@ -269,19 +275,29 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
         if (s != 0.f) atomicAdd(a.grad_x + (size_t)b * a.T + t0 + i, s);
       }
     };
-    // P += a3 * seed_t at the probe cells of my patch
+    // P += a3 * seed_t at the probe cells of my patch.  The common case (at most one probe per thread) needs one shared
+    // load and a compile-time unrolled select; further probes of the same thread go through the general loop.
     auto add_seeds = [&](float (&P)[R][4], int t) {
-      if (has_probe) {
-        for (int p = 0; p < a.n_prb; ++p)
-          if (pown[p] == tid) {
-            const float sv = ss[((t / TB) & 1) * TB * a.n_prb + (t % TB) * a.n_prb + p];
-            const int pc = pcell[p];
+      if (pc0 >= 0) {
+        const float* srow = ss + (t & (2 * TB - 1)) * a.n_prb;
+        const float sv = srow[pi0];
 #pragma unroll
-            for (int r = 0; r < R; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (pc == r * 4 + k) P[r][k] = fmaf(k3[r][k], sv, P[r][k]);
-          }
+          for (int k = 0; k < 4; ++k)
+            if (pc0 == r * 4 + k) P[r][k] = fmaf(k3[r][k], sv, P[r][k]);
+        if (more_probes) {
+          for (int p = pi0 + 1; p < a.n_prb; ++p)
+            if (pown[p] == tid) {
+              const float sw = srow[p];
+              const int pc = pcell[p];
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (pc == r * 4 + k) P[r][k] = fmaf(k3[r][k], sw, P[r][k]);
+            }
+        }
       }
     };
     if (tid == 0) {   // prime the tape ring
@@ -361,7 +377,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       }
       if (t > 0) ++L.npub;
       __syncthreads();
-      if (tid == 0 && it + RING < a.T) {   // every thread has read this slot: refill it RING steps ahead
+      if (tid == refill_tid && it + RING < a.T) {   // every thread has read this slot: refill it RING steps ahead
         mbar_expect_tx(full + slot, stage_bytes);
         bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(t - RING) * tape_step, stage_bytes, full + slot);
       }

@@ -234,8 +234,12 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
-  bool has_probe = false;
-  for (int p = 0; p < a.n_prb; ++p) has_probe |= (pown[p] == tid);
+  int pc0 = -1, pi0 = 0;
+  bool more_probes = false;
+  for (int p = 0; p < a.n_prb; ++p)
+    if (pown[p] == tid) {
+      if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
+    }
   const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
   const Scalars s = a.s;
 
@@ -294,17 +298,26 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
       const unsigned slot2 = (gi + 1) % RG, parity2 = ((gi + 1) / RG) & 1u;   // stage of step t-1: its u is my u_{t-2}
       float pv[R][4], g2[R][4];   // across the barrier: P (stencil centre), the new carry; lam holds c2 + own-cell part
       if (L.active) {
-        if (has_probe) {
-          for (int p = 0; p < a.n_prb; ++p)
-            if (pown[p] == tid) {
-              const float sv = ss[(blk & 1) * TB * a.n_prb + tt * a.n_prb + p];
-              const int pc = pcell[p];
+        if (pc0 >= 0) {   // lambda_t += dLoss/du_t through the probes (first probe of my patch: fast path)
+          const float* srow = ss + (blk & 1) * TB * a.n_prb + tt * a.n_prb;
+          const float sv = srow[pi0];
 #pragma unroll
-              for (int r = 0; r < R; ++r)
+          for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (pc == r * 4 + k) lam[r][k] += sv;
-            }
+            for (int k = 0; k < 4; ++k)
+              if (pc0 == r * 4 + k) lam[r][k] += sv;
+          if (more_probes) {
+            for (int p = pi0 + 1; p < a.n_prb; ++p)
+              if (pown[p] == tid) {
+                const float sw = srow[p];
+                const int pc = pcell[p];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (pc == r * 4 + k) lam[r][k] += sw;
+              }
+          }
         }
         if (a.grad_x && m1) {
           float sv = 0.f;
