@@ -154,6 +154,22 @@ int wt_step_backward(const wt_problem* p, const float* b, int b_batched, const f
                      const float* y1, const float* y2, const float* grad_y, float* grad_b, float* grad_c,
                      float* grad_y1, float* grad_y2, void* stream);
 
+/*
+ * Geometry parameterisation (the step before and after the loop): c = c0 + (c1-c0) * proj(blur^passes(rho)) and its
+ * reverse -- replaces WaveGeometryFreeForm._apply_blur / _apply_projection / .c (geom.py:207-233) and the autograd graph
+ * PyTorch builds from them.  taps: [(2*radius+1)^2] normalised disk stencil (the module's blur_kernel buffer);
+ * eta, beta, c0, c1: the module's 0-dim float32 device buffers (read on the device, no host synchronisation);
+ * blurred: [passes,Nx,Ny] out, every intermediate field (the last one is needed by wt_geom_backward).
+ */
+int wt_geom_forward(int Nx, int Ny, int radius, int passes, const float* rho, const float* taps, const float* eta,
+                    const float* beta, const float* c0, const float* c1, float* blurred, float* c_out, int device,
+                    void* stream);
+
+/* grad_rho [Nx,Ny] = d(sum(grad_c * c))/d rho; scratch: [2,Nx,Ny]. */
+int wt_geom_backward(int Nx, int Ny, int radius, int passes, const float* blurred_last, const float* grad_c,
+                     const float* taps, const float* eta, const float* beta, const float* c0, const float* c1,
+                     float* grad_rho, float* scratch, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

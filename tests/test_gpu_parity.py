@@ -545,3 +545,31 @@ def test_multi_pixel_probes_and_batched_line_source():
     ref = wo.probe_outputs(f["raw"], [False] * 3 + [True] * 3)
     ref = np.stack([ref[:, :, :3], ref[:, :, 3:]], axis=-1)
     assert rel_l2(out.detach().cpu().numpy(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("radius,passes,beta", [(1, 1, 100.0), (2, 2, 12.0), (3, 1, 30.0)])
+def test_fused_geometry_kernels_match_torch_path(radius, passes, beta, monkeypatch):
+    """wt_geom_forward/backward (row f-1) against the PyTorch evaluation of geom.py:207-233 on the same device."""
+    rng = np.random.RandomState(radius * 10 + passes)
+    Nx, Ny = 61, 53
+    rho0 = rng.rand(Nx, Ny).astype(np.float32)
+    w = torch.tensor(rng.randn(Nx, Ny).astype(np.float32), device=DEV)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("WT_GEOM_TORCH", mode)
+        g = wt.WaveGeometryFreeForm((Nx, Ny), 1.0, 1.0, 0.5, abs_N=4, abs_sig=5.0, abs_p=2.0, eta=0.45, beta=beta,
+                                    rho=torch.tensor(rho0), blur_radius=radius, blur_N=passes).to(DEV)
+        c = g.c
+        (c * w).sum().backward()
+        res[mode] = (c.detach().cpu().numpy(), g.rho.grad.cpu().numpy())
+    assert rel_l2(res["0"][0], res["1"][0]) < 1e-6
+    assert rel_l2(res["0"][1], res["1"][1]) < 1e-5
+    gold = load_golden("geometry")      # and against the reference fixture (radius 2, 2 passes, beta 12)
+    if (radius, passes) == (2, 2):
+        g = wt.WaveGeometryFreeForm((31, 29), 1.0, 1.0, 0.5, abs_N=4, abs_sig=5.0, abs_p=2.0, eta=0.45, beta=12.0,
+                                    design_region=torch.tensor(gold["free_design"]),
+                                    rho=torch.tensor(gold["free_rho_in"], dtype=torch.float32), blur_radius=2, blur_N=2).to(DEV)
+        c = g.c
+        (c * torch.tensor(gold["free_w_f32"], device=DEV)).sum().backward()
+        assert rel_l2(c.detach().cpu().numpy(), gold["free_c_f32"]) < 2e-6
+        assert rel_l2(g.rho.grad.cpu().numpy(), gold["free_grho_f32"]) < 2e-5

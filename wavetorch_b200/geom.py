@@ -6,6 +6,7 @@ once per forward in plain PyTorch on whatever device the module lives on, so aut
 CUDA adjoint back to `rho`.
 """
 import math
+import os
 from copy import deepcopy
 from typing import Tuple
 
@@ -26,6 +27,52 @@ def disk_pixels(r, c, radius, shape=None):
     if shape is not None:
         keep &= (rr >= 0) & (rr < shape[0]) & (cc >= 0) & (cc < shape[1])
     return rr[keep], cc[keep]
+
+
+class _FusedSpeed(torch.autograd.Function):
+    """c = c0 + (c1-c0) * proj(blur^N(rho)) in N fused CUDA launches (wt_geom_forward / wt_geom_backward); replaces
+    the ~50 elementwise launches PyTorch needs for geom.py:207-233 and their backward."""
+
+    @staticmethod
+    def forward(ctx, rho, taps, eta, beta, c0, c1, passes):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        dev = rho.device
+        Nx, Ny = rho.shape
+        radius = taps.shape[-1] // 2
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        rho32, taps32 = f32(rho), f32(taps).reshape(-1)
+        scal = [f32(t).reshape(1) for t in (eta, beta, c0, c1)]
+        blurred = torch.empty((passes, Nx, Ny), device=dev, dtype=torch.float32)
+        c = torch.empty((Nx, Ny), device=dev, dtype=torch.float32)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(dev):
+            st = lib.wt_geom_forward(Nx, Ny, radius, passes, _lib.ptr(rho32), _lib.ptr(taps32), *[_lib.ptr(t) for t in scal],
+                                     _lib.ptr(blurred), _lib.ptr(c), idx, _lib.stream_ptr(dev))
+        _lib.check(st, "wt_geom_forward")
+        _lib.count_launches(passes)
+        ctx.save_for_backward(blurred[passes - 1], taps32, *scal)
+        ctx.meta = (Nx, Ny, radius, passes, idx)
+        return c
+
+    @staticmethod
+    def backward(ctx, grad_c):
+        from . import _lib
+        lib = _lib.load()
+        last, taps32, eta, beta, c0, c1 = ctx.saved_tensors
+        Nx, Ny, radius, passes, idx = ctx.meta
+        dev = last.device
+        g = grad_c.detach().to(torch.float32).contiguous()
+        grad_rho = torch.empty((Nx, Ny), device=dev, dtype=torch.float32)
+        scratch = torch.empty((2, Nx, Ny), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            st = lib.wt_geom_backward(Nx, Ny, radius, passes, _lib.ptr(last), _lib.ptr(g), _lib.ptr(taps32), _lib.ptr(eta),
+                                      _lib.ptr(beta), _lib.ptr(c0), _lib.ptr(c1), _lib.ptr(grad_rho), _lib.ptr(scratch), idx,
+                                      _lib.stream_ptr(dev))
+        _lib.check(st, "wt_geom_backward")
+        _lib.count_launches(passes + 1)
+        return grad_rho, None, None, None, None, None, None
 
 
 def _tanh_projection(rho, eta, beta):
@@ -233,4 +280,11 @@ class WaveGeometryFreeForm(WaveGeometry):
 
     @property
     def c(self):
+        rho = self.rho
+        if rho.is_cuda and rho.dtype == torch.float32 and os.environ.get("WT_GEOM_TORCH", "0") != "1":
+            passes = getattr(self, "_blur_passes", None)
+            if passes is None:
+                passes = int(self.blur_N.item())
+            if passes >= 1 and self.blur_kernel.shape[-1] <= 11:
+                return _FusedSpeed.apply(rho, self.blur_kernel[0, 0], self.eta, self.beta, self.c0, self.c1, passes)
         return self.c0 + (self.c1 - self.c0) * self._rho_model()
