@@ -573,3 +573,42 @@ def test_fused_geometry_kernels_match_torch_path(radius, passes, beta, monkeypat
         (c * torch.tensor(gold["free_w_f32"], device=DEV)).sum().backward()
         assert rel_l2(c.detach().cpu().numpy(), gold["free_c_f32"]) < 2e-6
         assert rel_l2(g.rho.grad.cpu().numpy(), gold["free_grho_f32"]) < 2e-5
+
+
+@pytest.mark.parametrize("B,T", [(150, 33), (131, 1), (70, 2), (67, 130)])
+def test_more_samples_than_clusters(B, T):
+    """Persistent clusters loop over several samples (B > co-resident clusters): tape-ring parity, ghost-barrier phases
+    and gradient accumulation carry over from one sample to the next.  Checked against the streaming path."""
+    m = _vowel_model()
+    rng = np.random.RandomState(B + T)
+    x0 = (0.2 * rng.randn(B, T)).astype(np.float32)
+    w = torch.tensor(rng.randn(B, T, 3).astype(np.float32), device=DEV)
+    m.plan_flags = _lib.WT_F_FORCE_STREAM
+    xs = torch.tensor(x0, device=DEV, requires_grad=True)
+    o_ref = m(xs)
+    (o_ref * w).sum().backward()
+    g_ref, gx_ref = m.cell.geom.rho.grad.clone(), xs.grad.clone()
+    m.zero_grad()
+    m.plan_flags = _lib.WT_F_FORCE_RESIDENT
+    xr = torch.tensor(x0, device=DEV, requires_grad=True)
+    o = m(xr)
+    (o * w).sum().backward()
+    assert rel_l2(o.detach().cpu().numpy(), o_ref.detach().cpu().numpy()) < 1e-6
+    if T > 2:   # (the field has not reached the probes' neighbourhood earlier; gradients are ~0/0 noise)
+        assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g_ref.cpu().numpy()) < 2e-5
+    assert rel_l2(xr.grad.cpu().numpy(), gx_ref.cpu().numpy()) < 2e-5 or float(gx_ref.abs().max()) == 0.0
+
+
+def test_nonlinear_more_samples_than_clusters():
+    m = _vowel_model(0.1, 1.0, -30.0)
+    B, T = 90, 70
+    x0 = wo.synthetic_vowels(B, T)
+    w = torch.tensor(np.random.RandomState(1).randn(B, T, 3).astype(np.float32), device=DEV)
+    m.plan_flags = _lib.WT_F_FORCE_STREAM
+    o_ref = m(torch.tensor(x0, device=DEV)); (o_ref * w).sum().backward()
+    g_ref = m.cell.geom.rho.grad.clone()
+    m.zero_grad()
+    m.plan_flags = _lib.WT_F_FORCE_RESIDENT
+    o = m(torch.tensor(x0, device=DEV)); (o * w).sum().backward()
+    assert rel_l2(o.detach().cpu().numpy(), o_ref.detach().cpu().numpy()) < 1e-6
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g_ref.cpu().numpy()) < 2e-5
