@@ -472,7 +472,8 @@ size_t stream_ws_bwd_bytes(const wt_problem* p) {
   size_t plane = (size_t)p->Nx * p->Ny;
   size_t field = (size_t)p->B * plane;
   // coefficients (3) + accumulators (3) + two adjoint state fields + P + offsets
-  return (6 * plane + 3 * field) * sizeof(float) + (size_t)(p->n_src + p->n_prb + 4) * sizeof(int32_t) + 512;
+  size_t n = (6 * plane + 3 * field) * sizeof(float) + (size_t)(p->n_src + p->n_prb + 4) * sizeof(int32_t) + 512;
+  return ((n + 255) & ~(size_t)255) + tile_extra_ws_bwd_bytes(p);
 }
 
 struct Offsets {
@@ -586,6 +587,19 @@ int stream_backward(const wt_problem* p, const float* c, const float* b, const f
   if (!general) {
     k_coeff<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(b, c, (int)plane, p->dt, (p->dt * p->dt) / (p->h * p->h),
                                                               a1, a3, gs);
+    if (!grad_fields && tile_eligible(p) && vec4_ok(p, {l1, l2, history, workspace})) {
+      // large grid: K reverse steps per HBM round trip (wt_tile.cu), state kept as P = a3*lambda
+      size_t base = (6 * plane + 3 * field) * sizeof(float) + (size_t)(p->n_src + p->n_prb + 4) * sizeof(int32_t) + 512;
+      base = (base + 255) & ~(size_t)255;
+      float* extra = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + base);
+      float* spare1 = chained ? w1 : P;
+      float* spare2 = chained ? w2 : extra;
+      WT_TRY(tile_backward(p, a1, a3, c, src_ij, prb_ij, prb_sq, grad_probe, probe_raw, tape, l1, l2, spare1, spare2, Gc, grad_c,
+                           grad_x, chained, st));
+      if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
+      if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));
+      return WT_OK;
+    }
     const bool v4 = vec4_ok(p, {l1, l2, history, grad_fields, workspace});
     const int vec = v4 ? 4 : 1;
     const int nbz = pick_batch_chunks(p, vec);

@@ -44,15 +44,49 @@ struct TileArgs {
 
 constexpr int TILE_MAX_PRB = 32;
 constexpr int TILE_MAX_K = 8;
+constexpr int TILE_ADJ_K = 4;   // the adjoint keeps K steps of tape staged per thread: fixed depth
+
+// Ampere-style asynchronous copies: every thread stages ITS OWN patch of the next sample (and, in the adjoint, its tape
+// rows) while the current one is being advanced, so the only exposed HBM latency is that of a CTA's first sample.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool ok) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = ok ? 16 : 0;   // 0 source bytes: the 16 destination bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// a1/a3 of a thread's patch (zero outside the domain)
+template <int R>
+__device__ __forceinline__ void tile_load_coef(const float* __restrict__ a1, const float* __restrict__ a3, bool active, int gi0,
+                                               int gj0, int Nx, int Ny, float (&k1)[R][4], float (&k3)[R][4]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int gi = gi0 + r;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
+    if (active && gi >= 0 && gi < Nx && gj0 >= 0 && gj0 + 3 < Ny) {
+      p = __ldg(reinterpret_cast<const float4*>(a1 + (size_t)gi * Ny + gj0));
+      q = __ldg(reinterpret_cast<const float4*>(a3 + (size_t)gi * Ny + gj0));
+    }
+    k1[r][0] = p.x; k1[r][1] = p.y; k1[r][2] = p.z; k1[r][3] = p.w;
+    k3[r][0] = q.x; k3[r][1] = q.y; k3[r][2] = q.z; k3[r][3] = q.w;
+  }
+}
 
 template <int R>
 __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd(TileArgs a) {
   extern __shared__ float4 smem4[];
   const int slab = (a.EH + 2) * a.pitch;
   float* fld = reinterpret_cast<float*>(smem4);       // [2][slab], row 0 / EH+1 and the 4-float row pad stay zero
-  float* xs = fld + 2 * slab;                          // [TILE_MAX_K]
-  int* poff = reinterpret_cast<int*>(xs + TILE_MAX_K); // [TILE_MAX_PRB] smem offset of an owned probe
+  float* xs = fld + 2 * slab;                          // [2][TILE_MAX_K], double-buffered over samples
+  int* poff = reinterpret_cast<int*>(xs + 2 * TILE_MAX_K); // [TILE_MAX_PRB] smem offset of an owned probe
   int* pid = poff + TILE_MAX_PRB;                      // [TILE_MAX_PRB] its global index
+  float4* stg = reinterpret_cast<float4*>(pid + TILE_MAX_PRB);   // [2R][NT] staged patches of the next sample
   __shared__ int n_my_prb;
 
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -63,19 +97,30 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
   const int tile = blockIdx.x;
   const int ti0 = (tile / a.tiles_y) * a.TH, tj0 = (tile % a.tiles_y) * a.TW;   // owned tile origin
   const int gi0 = ti0 - a.K + lr0;                     // global row / col of my patch (may be outside the domain)
-  const int gj0 = tj0 - a.K + 4 * g;
+  const int gj0 = tj0 - a.K + 4 * g;                   // multiple of 4: a patch row is inside the domain or outside, never split
   const size_t plane = (size_t)a.Nx * a.Ny;
+  const int b_lo = blockIdx.y * a.bchunk, b_hi = min(a.B, b_lo + a.bchunk);
+
+  auto stage_sample = [&](int b) {
+    if (b < b_hi) {
+      const float* u1p = a.U1 + (size_t)b * plane;
+      const float* u2p = a.U2 + (size_t)b * plane;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int gi = gi0 + r;
+        const bool ok = active && gi >= 0 && gi < a.Nx && gj0 >= 0 && gj0 + 3 < a.Ny;
+        const size_t o = ok ? (size_t)gi * a.Ny + gj0 : 0;
+        cp_async16(&stg[r * NT + tid], u1p + o, ok);
+        cp_async16(&stg[(R + r) * NT + tid], u2p + o, ok);
+      }
+      if (tid < a.steps) cp_async4(&xs[(b & 1) * TILE_MAX_K + tid], a.x + (size_t)b * a.T + a.t0 + tid);
+    }
+    cp_async_commit();
+  };
+  stage_sample(b_lo);
 
   float k1[R][4], k3[R][4];
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int gi = gi0 + r, gj = gj0 + k;
-      const bool ok = active && gi >= 0 && gi < a.Nx && gj >= 0 && gj < a.Ny;
-      k1[r][k] = ok ? a.a1[(size_t)gi * a.Ny + gj] : 0.f;
-      k3[r][k] = ok ? a.a3[(size_t)gi * a.Ny + gj] : 0.f;
-    }
+  tile_load_coef<R>(a.a1, a.a3, active, gi0, gj0, a.Nx, a.Ny, k1, k3);
   unsigned m1 = 0, m2 = 0, m3 = 0;   // source listings of my cells: >=1, >=2, >=3 (more: handled by repeated adds below)
   if (active)
     for (int s = 0; s < a.n_src; ++s) {
@@ -105,31 +150,17 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
   // which of my cells belong to the owned tile (the ones written back)
   const bool col_in = (4 * g >= a.K) && (4 * g < a.K + a.TW) && (gj0 < a.Ny);
 
-  const int b_lo = blockIdx.y * a.bchunk, b_hi = min(a.B, b_lo + a.bchunk);
   for (int b = b_lo; b < b_hi; ++b) {
-    const float* u1p = a.U1 + (size_t)b * plane;
-    const float* u2p = a.U2 + (size_t)b * plane;
     float v[R][4], w[R][4];
+    cp_async_wait<0>();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int gi = gi0 + r;
-      const bool rok = active && gi >= 0 && gi < a.Nx;
-      if (rok && gj0 >= 0 && gj0 + 3 < a.Ny) {
-        const float4 p = *reinterpret_cast<const float4*>(u1p + (size_t)gi * a.Ny + gj0);
-        const float4 q = *reinterpret_cast<const float4*>(u2p + (size_t)gi * a.Ny + gj0);
-        v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
-        w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int gj = gj0 + k;
-          const bool ok = rok && gj >= 0 && gj < a.Ny;
-          v[r][k] = ok ? u1p[(size_t)gi * a.Ny + gj] : 0.f;
-          w[r][k] = ok ? u2p[(size_t)gi * a.Ny + gj] : 0.f;
-        }
-      }
+      const float4 p = stg[r * NT + tid], q = stg[(R + r) * NT + tid];
+      v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
+      w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
     }
-    if (tid < a.steps) xs[tid] = a.x[(size_t)b * a.T + a.t0 + tid];
+    stage_sample(b + 1);   // lands while this sample is advanced
+    const float* xsb = xs + (b & 1) * TILE_MAX_K;
     if (active) {
 #pragma unroll
       for (int r = 0; r < R; ++r)
@@ -164,7 +195,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         if (m1) {
-          const float xv = xs[j];
+          const float xv = xsb[j];
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -222,6 +253,279 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
 }
 
 // ------------------------------------------------------------------------------------------------
+// adjoint, temporally blocked.  State in HBM is P_t = a3*lambda_t (see wt_resident.cu: the adjoint recursion in P is the
+// forward update run backwards, the probe seeds are its sources).  One launch takes (P_t, P_{t+1}) at t = t_hi down
+// K steps; G' += L(u_{t-1}) * P_t is accumulated in registers over the K steps and the samples of the batch chunk.
+// ------------------------------------------------------------------------------------------------
+struct TileAdjArgs {
+  TileArgs g;                 // geometry, a1/a3, U1 = P_{t_hi}, U2 = P_{t_hi+1} (or the weighted carry), V1/V2 outputs,
+                              // t0 = t_hi, steps, src/prb lists, tape, probe_raw
+  const float* grad_probe;    // [B,T,n_prb]
+  float* G;                   // [plane] accumulator of sum L(u_{t-1}) * P_t
+  float* grad_x;              // nullable [B,T]
+  int premul_first;           // U2 of the first step is already weighted by (1-a1)
+  int atomic_G;
+};
+
+template <int R>
+__global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs aa) {
+  const TileArgs& a = aa.g;
+  extern __shared__ float4 smem4[];
+  const int slab = (a.EH + 2) * a.pitch;
+  float* fld = reinterpret_cast<float*>(smem4);
+  int* pown = reinterpret_cast<int*>(fld + 2 * slab);   // [TILE_MAX_PRB] owning thread of a probe inside the EXTENDED tile
+  int* pcel = pown + TILE_MAX_PRB;                      // its cell index inside the owner's patch
+  int* pid = pcel + TILE_MAX_PRB;                       // its global probe index
+  float4* stg = reinterpret_cast<float4*>(pid + TILE_MAX_PRB);   // [2R][NT] staged P_t, P_{t+1} patches of the next sample
+  __shared__ int n_my_prb;
+
+  const int tid = threadIdx.x, NT = blockDim.x;
+  float4* ring = stg + 2 * R * NT;                      // [TILE_ADJ_K][R][NT] staged tape rows, one slot per step of the block
+  const bool active = tid < a.nact;
+  const int run = tid / a.P4;
+  const int g = tid - run * a.P4;
+  const int lr0 = run * R;
+  const int tile = blockIdx.x;
+  const int ti0 = (tile / a.tiles_y) * a.TH, tj0 = (tile % a.tiles_y) * a.TW;
+  const int gi0 = ti0 - a.K + lr0;
+  const int gj0 = tj0 - a.K + 4 * g;
+  const size_t plane = (size_t)a.Nx * a.Ny;
+  const int b_lo = blockIdx.y * a.bchunk, b_hi = min(a.B, b_lo + a.bchunk);
+  const bool col_in = active && (4 * g >= a.K) && (4 * g < a.K + a.TW) && (gj0 < a.Ny);
+  bool own_row[R];                                      // rows of my patch that belong to the tile itself
+#pragma unroll
+  for (int r = 0; r < R; ++r) own_row[r] = col_in && lr0 + r >= a.K && lr0 + r < a.K + a.TH && gi0 + r < a.Nx;
+
+  // copy group j of sample b: the tape rows of reverse step j, plus (j == 0) the two state patches.  Exactly TILE_ADJ_K
+  // groups are committed per sample, empty ones included, so that "at most K-1 groups pending" always means "the oldest
+  // one has landed".
+  auto stage = [&](int b, int j) {
+    if (b < b_hi) {
+      if (j == 0) {
+        const float* u1p = a.U1 + (size_t)b * plane;
+        const float* u2p = a.U2 + (size_t)b * plane;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int gi = gi0 + r;
+          const bool ok = active && gi >= 0 && gi < a.Nx && gj0 >= 0 && gj0 + 3 < a.Ny;
+          const size_t o = ok ? (size_t)gi * a.Ny + gj0 : 0;
+          cp_async16(&stg[r * NT + tid], u1p + o, ok);
+          cp_async16(&stg[(R + r) * NT + tid], u2p + o, ok);
+        }
+      }
+      if (j < a.steps && col_in) {
+        const float* tb = a.tape + ((size_t)(a.t0 - j) * a.B + b) * plane;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          cp_async16(&ring[(j * R + r) * NT + tid], tb + (own_row[r] ? (size_t)(gi0 + r) * a.Ny + gj0 : 0), own_row[r]);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int j = 0; j < TILE_ADJ_K; ++j) stage(b_lo, j);
+
+  float k1[R][4], k3[R][4];
+  tile_load_coef<R>(a.a1, a.a3, active, gi0, gj0, a.Nx, a.Ny, k1, k3);
+  // sources among my OWNED cells (dLoss/dx gathers each source pixel exactly once)
+  unsigned m1 = 0, m2 = 0, m3 = 0;
+  if (aa.grad_x && col_in)
+    for (int s = 0; s < a.n_src; ++s) {
+      const int si = a.src_ij[2 * s] - gi0, sj = a.src_ij[2 * s + 1] - gj0;
+      if (si >= 0 && si < R && sj >= 0 && sj < 4 && lr0 + si >= a.K && lr0 + si < a.K + a.TH) {
+        const unsigned bit = 1u << (si * 4 + sj);
+        if (m2 & bit) m3 |= bit; else if (m1 & bit) m2 |= bit; else m1 |= bit;
+      }
+    }
+  if (tid == 0) {   // probes anywhere in the extended tile: their seeds drive the ghost region too
+    int n = 0;
+    for (int p = 0; p < a.n_prb && n < TILE_MAX_PRB; ++p) {
+      const int pi = a.prb_ij[2 * p] - (ti0 - a.K), pj = a.prb_ij[2 * p + 1] - (tj0 - a.K);
+      if (pi >= 0 && pi < a.EH && pj >= 0 && pj < a.EW) {
+        pown[n] = (pi / R) * a.P4 + pj / 4;
+        pcel[n] = (pi % R) * 4 + (pj & 3);
+        pid[n] = p;
+        ++n;
+      }
+    }
+    n_my_prb = n;
+  }
+  for (int i = tid; i < 2 * slab; i += NT) fld[i] = 0.f;
+  __syncthreads();
+  int my_np = 0;
+  for (int p = 0; p < n_my_prb; ++p) my_np += (pown[p] == tid);
+  const int own = (lr0 + 1) * a.pitch + 4 + 4 * g;
+
+  float G[R][4];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) G[r][k] = 0.f;
+
+  for (int b = b_lo; b < b_hi; ++b) {
+    float v[R][4], w[R][4];
+    cp_async_wait<TILE_ADJ_K - 1>();   // group 0 of this sample
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 p = stg[r * NT + tid], q = stg[(R + r) * NT + tid];
+      v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
+      w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
+    }
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        *reinterpret_cast<float4*>(fld + (lr0 + r + 1) * a.pitch + 4 + 4 * g) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+    }
+    __syncthreads();
+
+    // one reverse step: cu = P_t (kept), pr = P_{t+1} (or the weighted carry) on entry and P_{t-1} on exit
+    auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int j) {
+      const int t = a.t0 - j;
+      const float* cur = fld + (j & 1) * slab;
+      float* nxt = fld + ((j + 1) & 1) * slab;
+      if (active) {
+        if (m1) {   // dLoss/dx[b,t] = sum over source pixels of lambda_t = P_t / a3
+          float sx = 0.f;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (m1 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
+              if (m2 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
+              if (m3 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
+            }
+          atomicAdd(aa.grad_x + (size_t)b * a.T + t, sx);
+        }
+        if (j > 0) cp_async_wait<TILE_ADJ_K - 1>();   // tape rows of this step
+        if (col_in) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 tp = ring[(j * R + r) * NT + tid];   // zero-filled where the row is not mine
+            G[r][0] = fmaf(tp.x, cu[r][0], G[r][0]);
+            G[r][1] = fmaf(tp.y, cu[r][1], G[r][1]);
+            G[r][2] = fmaf(tp.z, cu[r][2], G[r][2]);
+            G[r][3] = fmaf(tp.w, cu[r][3], G[r][3]);
+          }
+        }
+      }
+      stage(b + 1, j);   // refill the slots just consumed with the next sample's
+      if (active) {
+        const float* ownp = cur + own;
+        const float4 up = *reinterpret_cast<const float4*>(ownp - a.pitch);
+        const float4 dn = *reinterpret_cast<const float4*>(ownp + R * a.pitch);
+        const float upv[4] = {up.x, up.y, up.z, up.w};
+        const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+        const bool premul = aa.premul_first && j == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float lf = ownp[r * a.pitch - 1], rt = ownp[r * a.pitch + 4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float n = (r == 0) ? upv[k] : cu[r - 1][k];
+            const float s = (r == R - 1) ? dnv[k] : cu[r + 1][k];
+            const float wv = (k == 0) ? lf : cu[r][k - 1];
+            const float e = (k == 3) ? rt : cu[r][k + 1];
+            const float lap = fmaf(-4.f, cu[r][k], (n + s) + (wv + e));
+            pr[r][k] = premul ? fmaf(k3[r][k], lap, fmaf(k1[r][k], cu[r][k], pr[r][k]))
+                              : wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap);
+          }
+        }
+        if (my_np && t > 0) {   // P_{t-1} += a3 * seed_{t-1}
+          for (int p = 0; p < n_my_prb; ++p)
+            if (pown[p] == tid) {
+              const size_t o = ((size_t)b * a.T + (t - 1)) * a.n_prb + pid[p];
+              float sv = aa.grad_probe[o];
+              if (a.prb_sq[pid[p]]) sv *= 2.f * a.probe_raw[o];
+              const int pc = pcel[p];
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (pc == r * 4 + k) pr[r][k] = fmaf(k3[r][k], sv, pr[r][k]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          *reinterpret_cast<float4*>(nxt + (lr0 + r + 1) * a.pitch + 4 + 4 * g) = make_float4(pr[r][0], pr[r][1], pr[r][2], pr[r][3]);
+      }
+      __syncthreads();
+    };
+    int j = 0;
+    for (; j + 1 < a.steps; j += 2) {
+      step(v, w, j);
+      step(w, v, j + 1);
+    }
+    bool latest_in_v = true;
+    if (j < a.steps) { step(v, w, j); latest_in_v = false; ++j; }
+    for (; j < TILE_ADJ_K; ++j) stage(b + 1, j);   // short last block: keep the group count per sample fixed
+    if (col_in) {   // owned tile back to HBM: V1 = P_{t_hi-steps}, V2 = P_{t_hi-steps+1}
+      float* o1 = a.V1 + (size_t)b * plane;
+      float* o2 = a.V2 + (size_t)b * plane;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (own_row[r]) {
+          const int gi = gi0 + r;
+          const float4 hi = latest_in_v ? make_float4(v[r][0], v[r][1], v[r][2], v[r][3]) : make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
+          const float4 lo = latest_in_v ? make_float4(w[r][0], w[r][1], w[r][2], w[r][3]) : make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+          *reinterpret_cast<float4*>(o1 + (size_t)gi * a.Ny + gj0) = hi;
+          *reinterpret_cast<float4*>(o2 + (size_t)gi * a.Ny + gj0) = lo;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  if (col_in) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (own_row[r]) {
+        float* gp = aa.G + (size_t)(gi0 + r) * a.Ny + gj0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (aa.atomic_G) atomicAdd(gp + k, G[r][k]);
+          else gp[k] += G[r][k];
+        }
+      }
+    }
+  }
+}
+
+// lambda-form <-> P-form conversions at the ends of a (possibly chained) backward call
+__global__ void k_to_pform(float* __restrict__ f1, float* __restrict__ f2, const float* __restrict__ a3, size_t plane, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float k = a3[i % plane];
+    f1[i] *= k;      // P_{T-1} (before its seed) = a3 * dLoss/du_{T-1}
+    f2[i] *= k;      // a3 * (1-a1)*lambda_T : the weighted carry stays weighted
+  }
+}
+__global__ void k_from_pform(float* __restrict__ pm1, float* __restrict__ p0, const float* __restrict__ a1,
+                             const float* __restrict__ a3, size_t plane, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float k = a3[i % plane];
+    const float inv = k != 0.f ? 1.f / k : 0.f;
+    pm1[i] = pm1[i] * inv;                               // dLoss/du1_in = lambda_{-1}
+    p0[i] = (1.f - a1[i % plane]) * p0[i] * inv;          // dLoss/du2_in = (1-a1) * lambda_0
+  }
+}
+// P_{T-1} += a3 * seed_{T-1}; one block per sample
+__global__ void k_seed_pform(float* __restrict__ P, size_t plane, int Ny, const float* __restrict__ a3,
+                             const float* __restrict__ grad_probe, const float* __restrict__ probe_raw, int t, int T,
+                             const int32_t* __restrict__ prb_ij, const int32_t* __restrict__ prb_sq, int n_prb) {
+  const int b = blockIdx.x;
+  for (int p = threadIdx.x; p < n_prb; p += blockDim.x) {
+    const size_t o = ((size_t)b * T + t) * n_prb + p;
+    float g = grad_probe[o];
+    if (prb_sq[p]) g *= 2.f * probe_raw[o];
+    const size_t cell = (size_t)prb_ij[2 * p] * Ny + prb_ij[2 * p + 1];
+    atomicAdd(P + (size_t)b * plane + cell, a3[cell] * g);
+  }
+}
+__global__ void k_finish_grad_c(const float* __restrict__ G, const float* __restrict__ c, size_t plane, float* __restrict__ grad_c) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < plane) grad_c[i] = 2.f * G[i] / c[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 bool tile_eligible(const wt_problem* p) {
@@ -241,11 +545,12 @@ size_t tile_extra_ws_bytes(const wt_problem* p) {
 
 struct TileGeom { int K, R, TH, TW, EH, EW, P4, pitch, runs, nact, threads, tiles_x, tiles_y; size_t smem; };
 
-static TileGeom tile_geom(const wt_problem* p) {
+static TileGeom tile_geom(const wt_problem* p, int force_K = 0) {
   TileGeom t;
   const char* ek = getenv("WT_TILE_K");
   t.K = ek ? atoi(ek) : 4;
   if (t.K != 8) t.K = 4;
+  if (force_K) t.K = force_K;
   t.R = 4;
   const char* er = getenv("WT_TILE_R");
   if (er) t.R = atoi(er);
@@ -262,7 +567,7 @@ static TileGeom tile_geom(const wt_problem* p) {
   t.threads = t.nact;
   t.tiles_x = (p->Nx + t.TH - 1) / t.TH;
   t.tiles_y = (p->Ny + t.TW - 1) / t.TW;
-  t.smem = (size_t)2 * (t.EH + 2) * t.pitch * 4 + TILE_MAX_K * 4 + 2 * TILE_MAX_PRB * 4 + 64;
+  t.smem = (size_t)2 * (t.EH + 2) * t.pitch * 4 + 2 * TILE_MAX_K * 4 + 2 * TILE_MAX_PRB * 4 + (size_t)2 * t.R * t.threads * 16 + 64;
   return t;
 }
 
@@ -315,6 +620,77 @@ int tile_forward(const wt_problem* p, const float* a1, const float* a3, const fl
     WT_CUDA(cudaMemcpyAsync(u2, A2, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   if (launches) *launches = n;
+  return WT_OK;
+}
+
+
+size_t tile_extra_ws_bwd_bytes(const wt_problem* p) {
+  // one more [B,plane] field so that (adj1,adj2)/(w1,w2) always have a ping-pong partner pair
+  return tile_eligible(p) ? (size_t)p->B * p->Nx * p->Ny * sizeof(float) + 256 : 0;
+}
+
+// state1/state2: in  lambda-form (dLoss/du_{T-1} without its seed, weighted carry) -- zeros when not chained
+//                out lambda-form (dLoss/du1_in, dLoss/du2_in)
+// spare1/spare2: two more [B,plane] buffers; G: zeroed [plane] accumulator
+int tile_backward(const wt_problem* p, const float* a1, const float* a3, const float* c, const int32_t* src_ij,
+                  const int32_t* prb_ij, const int32_t* prb_sq, const float* grad_probe, const float* probe_raw,
+                  const float* tape, float* state1, float* state2, float* spare1, float* spare2, float* G, float* grad_c,
+                  float* grad_x, bool chained, cudaStream_t st) {
+  const TileGeom g = tile_geom(p, TILE_ADJ_K);
+  const size_t plane = (size_t)p->Nx * p->Ny, field = plane * p->B;
+  if (grad_x) WT_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)p->B * p->T * sizeof(float), st));
+  if (chained) k_to_pform<<<592, 256, 0, st>>>(state1, state2, a3, plane, field);
+  k_seed_pform<<<p->B, 64, 0, st>>>(state1, plane, p->Ny, a3, grad_probe, probe_raw, p->T - 1, p->T, prb_ij, prb_sq, p->n_prb);
+  TileAdjArgs aa = {};
+  TileArgs& a = aa.g;
+  a.Nx = p->Nx; a.Ny = p->Ny; a.B = p->B; a.T = p->T; a.K = g.K;
+  a.TH = g.TH; a.TW = g.TW; a.EH = g.EH; a.EW = g.EW; a.P4 = g.P4; a.pitch = g.pitch; a.runs = g.runs; a.nact = g.nact;
+  a.tiles_y = g.tiles_y; a.n_src = p->n_src; a.n_prb = p->n_prb;
+  a.a1 = a1; a.a3 = a3; a.src_ij = src_ij; a.prb_ij = prb_ij; a.prb_sq = prb_sq;
+  a.probe_raw = const_cast<float*>(probe_raw); a.tape = const_cast<float*>(tape);
+  aa.grad_probe = grad_probe; aa.G = G; aa.grad_x = grad_x;
+  const int ntiles = g.tiles_x * g.tiles_y;
+  int nby = (148 * 8 + ntiles - 1) / ntiles;
+  if (nby < 1) nby = 1;
+  if (nby > p->B) nby = p->B;
+  a.bchunk = (p->B + nby - 1) / nby;
+  nby = (p->B + a.bchunk - 1) / a.bchunk;
+  aa.atomic_G = nby > 1;
+  const size_t smem = (size_t)2 * (g.EH + 2) * g.pitch * 4 + 3 * TILE_MAX_PRB * 4 + (size_t)(2 + TILE_ADJ_K) * g.R * g.threads * 16 + 64;
+  float* A1 = state1; float* A2 = state2; float* B1 = spare1; float* B2 = spare2;
+  for (int t_hi = p->T - 1; t_hi >= 0; t_hi -= g.K) {
+    a.t0 = t_hi;
+    a.steps = t_hi + 1 < g.K ? t_hi + 1 : g.K;
+    a.U1 = A1; a.U2 = A2; a.V1 = B1; a.V2 = B2;
+    aa.premul_first = (t_hi == p->T - 1) ? 1 : 0;
+    dim3 grid(ntiles, nby), block(g.threads);
+    switch (g.R) {
+      case 2:
+        WT_CUDA(cudaFuncSetAttribute(k_tile_adj<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_adj<2><<<grid, block, smem, st>>>(aa);
+        break;
+      case 3:
+        WT_CUDA(cudaFuncSetAttribute(k_tile_adj<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_adj<3><<<grid, block, smem, st>>>(aa);
+        break;
+      default:
+        WT_CUDA(cudaFuncSetAttribute(k_tile_adj<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_adj<4><<<grid, block, smem, st>>>(aa);
+        break;
+    }
+    float* s1 = A1; float* s2 = A2; A1 = B1; A2 = B2; B1 = s1; B2 = s2;
+  }
+  WT_CUDA(cudaGetLastError());
+  // now A1 = P_{-1}, A2 = P_0
+  k_finish_grad_c<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(G, c, plane, grad_c);
+  if (chained) {
+    k_from_pform<<<592, 256, 0, st>>>(A1, A2, a1, a3, plane, field);
+    if (A1 != state1) {
+      WT_CUDA(cudaMemcpyAsync(state1, A1, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      WT_CUDA(cudaMemcpyAsync(state2, A2, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  WT_CUDA(cudaGetLastError());
   return WT_OK;
 }
 
