@@ -5,6 +5,7 @@
 #include "wt_common.cuh"
 #include "wt_resident.h"
 #include "wt_stream.h"
+#include "wt_tile.h"
 
 namespace wt {
 
@@ -69,6 +70,10 @@ static int make_plan(const wt_problem* p, bool need_adjoint, bool need_general, 
   const bool general = plan->nonlinear || (p->flags & WT_F_NEED_GRAD_B);
   plan->launches_fwd = 2 * p->T + 4;
   plan->launches_bwd = (general ? 3 : 2) * p->T + 6;
+  if (tile_eligible(p)) {   // temporally blocked kernels (wt_tile.cu); dLoss/dfields requests still go per step
+    plan->launches_fwd = tile_launches_fwd(p) + 3;
+    plan->launches_bwd = tile_launches_bwd(p) + 3;
+  }
   return WT_OK;
 }
 

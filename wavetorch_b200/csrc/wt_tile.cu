@@ -265,6 +265,8 @@ struct TileAdjArgs {
   float* grad_x;              // nullable [B,T]
   int premul_first;           // U2 of the first step is already weighted by (1-a1)
   int atomic_G;
+  int in_lambda;              // U1/U2 hold lambda (the wt_backward adj1/adj2 convention): scale by a3 on load
+  int out_lambda;             // last launch of a chained call: V1 = dLoss/du1_in = P_{-1}/a3, V2 = dLoss/du2_in = (1-a1)*P_0/a3
 };
 
 template <int R>
@@ -371,6 +373,12 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
       v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
       w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
     }
+    if (aa.in_lambda) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[r][k] *= k3[r][k]; w[r][k] *= k3[r][k]; }
+    }
     if (active) {
 #pragma unroll
       for (int r = 0; r < R; ++r)
@@ -465,8 +473,13 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
       for (int r = 0; r < R; ++r) {
         if (own_row[r]) {
           const int gi = gi0 + r;
-          const float4 hi = latest_in_v ? make_float4(v[r][0], v[r][1], v[r][2], v[r][3]) : make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
-          const float4 lo = latest_in_v ? make_float4(w[r][0], w[r][1], w[r][2], w[r][3]) : make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+          float4 hi = latest_in_v ? make_float4(v[r][0], v[r][1], v[r][2], v[r][3]) : make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
+          float4 lo = latest_in_v ? make_float4(w[r][0], w[r][1], w[r][2], w[r][3]) : make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+          if (aa.out_lambda) {
+            hi.x /= k3[r][0]; hi.y /= k3[r][1]; hi.z /= k3[r][2]; hi.w /= k3[r][3];
+            lo.x = (1.f - k1[r][0]) * lo.x / k3[r][0]; lo.y = (1.f - k1[r][1]) * lo.y / k3[r][1];
+            lo.z = (1.f - k1[r][2]) * lo.z / k3[r][2]; lo.w = (1.f - k1[r][3]) * lo.w / k3[r][3];
+          }
           *reinterpret_cast<float4*>(o1 + (size_t)gi * a.Ny + gj0) = hi;
           *reinterpret_cast<float4*>(o2 + (size_t)gi * a.Ny + gj0) = lo;
         }
@@ -490,26 +503,9 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
   }
 }
 
-// lambda-form <-> P-form conversions at the ends of a (possibly chained) backward call
-__global__ void k_to_pform(float* __restrict__ f1, float* __restrict__ f2, const float* __restrict__ a3, size_t plane, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float k = a3[i % plane];
-    f1[i] *= k;      // P_{T-1} (before its seed) = a3 * dLoss/du_{T-1}
-    f2[i] *= k;      // a3 * (1-a1)*lambda_T : the weighted carry stays weighted
-  }
-}
-__global__ void k_from_pform(float* __restrict__ pm1, float* __restrict__ p0, const float* __restrict__ a1,
-                             const float* __restrict__ a3, size_t plane, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float k = a3[i % plane];
-    const float inv = k != 0.f ? 1.f / k : 0.f;
-    pm1[i] = pm1[i] * inv;                               // dLoss/du1_in = lambda_{-1}
-    p0[i] = (1.f - a1[i % plane]) * p0[i] * inv;          // dLoss/du2_in = (1-a1) * lambda_0
-  }
-}
-// P_{T-1} += a3 * seed_{T-1}; one block per sample
-__global__ void k_seed_pform(float* __restrict__ P, size_t plane, int Ny, const float* __restrict__ a3,
-                             const float* __restrict__ grad_probe, const float* __restrict__ probe_raw, int t, int T,
+// lambda_{T-1} += seed_{T-1} (the first blocked launch scales by a3 on load); one block per sample
+__global__ void k_seed_last(float* __restrict__ L, size_t plane, int Ny,
+                            const float* __restrict__ grad_probe, const float* __restrict__ probe_raw, int t, int T,
                              const int32_t* __restrict__ prb_ij, const int32_t* __restrict__ prb_sq, int n_prb) {
   const int b = blockIdx.x;
   for (int p = threadIdx.x; p < n_prb; p += blockDim.x) {
@@ -517,7 +513,7 @@ __global__ void k_seed_pform(float* __restrict__ P, size_t plane, int Ny, const 
     float g = grad_probe[o];
     if (prb_sq[p]) g *= 2.f * probe_raw[o];
     const size_t cell = (size_t)prb_ij[2 * p] * Ny + prb_ij[2 * p + 1];
-    atomicAdd(P + (size_t)b * plane + cell, a3[cell] * g);
+    atomicAdd(L + (size_t)b * plane + cell, g);
   }
 }
 __global__ void k_finish_grad_c(const float* __restrict__ G, const float* __restrict__ c, size_t plane, float* __restrict__ grad_c) {
@@ -624,6 +620,10 @@ int tile_forward(const wt_problem* p, const float* a1, const float* a3, const fl
 }
 
 
+// kernel launches of one tile_forward / tile_backward call (setup kernels of the caller not included)
+int tile_launches_fwd(const wt_problem* p) { const int K = tile_geom(p).K; return (p->T + K - 1) / K + 1; }
+int tile_launches_bwd(const wt_problem* p) { return (p->T + TILE_ADJ_K - 1) / TILE_ADJ_K + 2; }
+
 size_t tile_extra_ws_bwd_bytes(const wt_problem* p) {
   // one more [B,plane] field so that (adj1,adj2)/(w1,w2) always have a ping-pong partner pair
   return tile_eligible(p) ? (size_t)p->B * p->Nx * p->Ny * sizeof(float) + 256 : 0;
@@ -639,8 +639,7 @@ int tile_backward(const wt_problem* p, const float* a1, const float* a3, const f
   const TileGeom g = tile_geom(p, TILE_ADJ_K);
   const size_t plane = (size_t)p->Nx * p->Ny, field = plane * p->B;
   if (grad_x) WT_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)p->B * p->T * sizeof(float), st));
-  if (chained) k_to_pform<<<592, 256, 0, st>>>(state1, state2, a3, plane, field);
-  k_seed_pform<<<p->B, 64, 0, st>>>(state1, plane, p->Ny, a3, grad_probe, probe_raw, p->T - 1, p->T, prb_ij, prb_sq, p->n_prb);
+  k_seed_last<<<p->B, 64, 0, st>>>(state1, plane, p->Ny, grad_probe, probe_raw, p->T - 1, p->T, prb_ij, prb_sq, p->n_prb);
   TileAdjArgs aa = {};
   TileArgs& a = aa.g;
   a.Nx = p->Nx; a.Ny = p->Ny; a.B = p->B; a.T = p->T; a.K = g.K;
@@ -662,7 +661,8 @@ int tile_backward(const wt_problem* p, const float* a1, const float* a3, const f
     a.t0 = t_hi;
     a.steps = t_hi + 1 < g.K ? t_hi + 1 : g.K;
     a.U1 = A1; a.U2 = A2; a.V1 = B1; a.V2 = B2;
-    aa.premul_first = (t_hi == p->T - 1) ? 1 : 0;
+    aa.premul_first = aa.in_lambda = (t_hi == p->T - 1) ? 1 : 0;
+    aa.out_lambda = (chained && t_hi - g.K < 0) ? 1 : 0;
     dim3 grid(ntiles, nby), block(g.threads);
     switch (g.R) {
       case 2:
@@ -684,8 +684,7 @@ int tile_backward(const wt_problem* p, const float* a1, const float* a3, const f
   // now A1 = P_{-1}, A2 = P_0
   k_finish_grad_c<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(G, c, plane, grad_c);
   if (chained) {
-    k_from_pform<<<592, 256, 0, st>>>(A1, A2, a1, a3, plane, field);
-    if (A1 != state1) {
+    if (A1 != state1) {   // odd number of launches: the result sits in the spare pair
       WT_CUDA(cudaMemcpyAsync(state1, A1, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
       WT_CUDA(cudaMemcpyAsync(state2, A2, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }

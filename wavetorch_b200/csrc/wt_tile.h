@@ -11,6 +11,8 @@ int tile_forward(const wt_problem* p, const float* a1, const float* a3, const fl
                  float* tape, float* extra_ws, cudaStream_t st, int* launches);
 
 size_t tile_extra_ws_bwd_bytes(const wt_problem* p);
+int tile_launches_fwd(const wt_problem* p);
+int tile_launches_bwd(const wt_problem* p);
 int tile_backward(const wt_problem* p, const float* a1, const float* a3, const float* c, const int32_t* src_ij,
                   const int32_t* prb_ij, const int32_t* prb_sq, const float* grad_probe, const float* probe_raw,
                   const float* tape, float* state1, float* state2, float* spare1, float* spare2, float* G, float* grad_c,

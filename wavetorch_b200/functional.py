@@ -138,6 +138,8 @@ class _CheckpointedLoop(torch.autograd.Function):
             return None, None, None, zero, None
         lib = _lib.load()
         spec, segs, chunks, ckpts = ctx.spec, ctx.segs, ctx.chunks, ctx.ckpts
+        if ckpts is None:
+            ckpts = {}
         x32, c32, b32, rho32 = ctx.saved
         dev = c32.device
         B, T = x32.shape
@@ -159,7 +161,10 @@ class _CheckpointedLoop(torch.autograd.Function):
                 prob = _CheckpointedLoop._problem(spec, Nx, Ny, nb, s1 - s0, dev, k == 0, bool(need[2]))
                 plan = _lib.query_plan(prob)
                 if k > 0:
-                    u1, u2 = (t.clone() for t in ckpts[(ci, k)])
+                    if ckpts.get((ci, k)) is None:
+                        raise RuntimeError("wavetorch_b200: the checkpoints of this graph were consumed by an earlier "
+                                           "backward(); run the forward again")
+                    u1, u2 = ckpts.pop((ci, k))      # advanced in place by the recomputation: used exactly once
                 else:
                     u1 = torch.empty((nb, Nx, Ny), device=dev, dtype=torch.float32)
                     u2 = torch.empty_like(u1)
