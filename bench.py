@@ -218,10 +218,14 @@ def run_ours(args):
     labels_host = ((torch.arange(B) + rank * B) % 3).pin_memory()
     x_dev, labels = x_host.to(dev), labels_host.to(dev)
 
+    def loss_head(out, y):
+        """train.py:61-62 -- CrossEntropy(normalize_power(sum_t I), y) -- as the fused head (wavetorch_b200/loss.py)."""
+        return wt.power_cross_entropy(out, y)[0]
+
     def train_step(x, y):
         opt.zero_grad(set_to_none=True)
         out = runner(x)
-        loss = torch.nn.functional.cross_entropy(wt.utils.normalize_power(out.sum(dim=1)), y)
+        loss = loss_head(out, y)
         loss.backward()
         opt.step()
         model.cell.geom.constrain_to_design_region()
@@ -262,7 +266,7 @@ def run_ours(args):
             from wavetorch_b200.graph import GraphedTrainStep
             opt_g = torch.optim.Adam(model.parameters(), lr=4e-4, capturable=True)
             graphed = GraphedTrainStep(
-                runner, opt_g, lambda out, y: torch.nn.functional.cross_entropy(wt.utils.normalize_power(out.sum(dim=1)), y),
+                runner, opt_g, loss_head,
                 x_dev, labels, warmup=max(args.warmup, 3))
             graphed(x_dev, labels)
             mode = "cuda-graph"
@@ -305,7 +309,7 @@ def run_ours(args):
 
     # dominant kernels, timed alone with CUDA events on the launching stream
     out = model(x_dev)
-    loss = torch.nn.functional.cross_entropy(wt.utils.normalize_power(out.sum(dim=1)), labels)
+    loss = loss_head(out, labels)
     (gout,) = torch.autograd.grad(loss, out, retain_graph=True)
 
     def fwd_tape():

@@ -170,6 +170,22 @@ int wt_geom_backward(int Nx, int Ny, int radius, int passes, const float* blurre
                      const float* taps, const float* eta, const float* beta, const float* c0, const float* c1,
                      float* grad_rho, float* scratch, int device, void* stream);
 
+/*
+ * Loss head of the classifier (the step after the loop and before its adjoint): replaces
+ *     loss = CrossEntropyLoss()(normalize_power(model(x).sum(dim=1)), labels)      train.py:61-62, utils.py:35-36
+ * and its autograd graph.
+ *   probe_out [B,T,P]  the loop output;  labels [B] int64 class indices in [0,P)
+ *   B_total            samples the mean runs over (this call's B of them; 0 = B) -- a batch shard passes the global batch
+ *   loss      [1]      sum of this call's cross entropies / B_total;  y_pred [B,P] normalised probe powers (nullable)
+ *   dlds      [B,P]    out: dLoss/d(sum_t probe_out[b,:,p]), consumed by wt_loss_backward
+ *   scratch   [B]
+ * wt_loss_backward: grad_probe[b,t,p] = grad_loss * dlds[b,p]   (grad_loss: device scalar, NULL = 1).
+ */
+int wt_loss_forward(int B, int T, int P, int B_total, const float* probe_out, const int64_t* labels, float* loss,
+                    float* y_pred, float* dlds, float* scratch, int device, void* stream);
+int wt_loss_backward(int B, int T, int P, const float* dlds, const float* grad_loss, float* grad_probe, int device,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

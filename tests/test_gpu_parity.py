@@ -618,3 +618,44 @@ def test_nonlinear_more_samples_than_clusters():
     o = m(torch.tensor(x0, device=DEV)); (o * w).sum().backward()
     assert rel_l2(o.detach().cpu().numpy(), o_ref.detach().cpu().numpy()) < 1e-6
     assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g_ref.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,P", [(64, 1000, 3), (5, 37, 5), (1, 1, 1), (7, 513, 10)])
+def test_fused_loss_head_matches_torch_ops(B, T, P):
+    """wt_loss_forward/backward against the reference's own ops (train.py:61-62, utils.py:35-36):
+    CrossEntropyLoss()(normalize_power(out.sum(dim=1)), labels), its prediction output and its gradient w.r.t. out."""
+    rng = np.random.RandomState(B * 1000 + T + P)
+    out0 = torch.tensor((rng.rand(B, T, P) ** 2).astype(np.float32), device=DEV)
+    lab = torch.tensor(rng.randint(0, P, size=B), device=DEV)
+    o1 = out0.clone().requires_grad_(True)
+    pred_ref = wt.utils.normalize_power(o1.sum(dim=1))
+    loss_ref = torch.nn.functional.cross_entropy(pred_ref, lab)
+    (3.0 * loss_ref).backward()
+    o2 = out0.clone().requires_grad_(True)
+    loss, pred = wt.power_cross_entropy(o2, lab)
+    (3.0 * loss).backward()
+    assert not pred.requires_grad
+    assert abs(loss.item() - loss_ref.item()) <= 2e-6 * max(1.0, abs(loss_ref.item()))
+    assert rel_l2(pred.cpu().numpy(), pred_ref.detach().cpu().numpy()) < 1e-6
+    if P > 1:
+        assert rel_l2(o2.grad.cpu().numpy(), o1.grad.cpu().numpy()) < 2e-5
+    else:
+        assert float(o2.grad.abs().max()) < 1e-6
+    # a shard of a larger batch: mean over batch_total
+    loss_half, _ = wt.power_cross_entropy(out0, lab, batch_total=2 * B)
+    assert abs(loss_half.item() - 0.5 * loss_ref.item()) <= 2e-6
+    # a label outside [0, P) poisons the loss
+    bad = lab.clone(); bad[0] = P
+    assert torch.isnan(wt.power_cross_entropy(out0, bad)[0])
+
+
+def test_fused_loss_head_in_training_step_matches_torch_head():
+    """One training iteration of config 3 with the fused head vs the torch-op head: same loss, same rho.grad."""
+    B, T = 6, 300
+    x = torch.tensor(wo.synthetic_vowels(B, T), device=DEV)
+    y = torch.arange(B, device=DEV) % 3
+    m1, m2 = _vowel_model(), _vowel_model()
+    l1 = torch.nn.functional.cross_entropy(wt.utils.normalize_power(m1(x).sum(dim=1)), y); l1.backward()
+    l2, _ = wt.power_cross_entropy(m2(x), y); l2.backward()
+    assert abs(l1.item() - l2.item()) < 1e-6
+    assert rel_l2(m2.cell.geom.rho.grad.cpu().numpy(), m1.cell.geom.rho.grad.cpu().numpy()) < 1e-5

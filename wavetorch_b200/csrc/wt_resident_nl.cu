@@ -16,9 +16,15 @@ constexpr int res_nl_max_threads() {
   return R <= 2 ? 512 : R == 3 ? 448 : 384;   // register budget: the nonlinear adjoint keeps ~9 values per cell live
 }
 
+// Per-cell constants of the nonlinear coefficients, kept in registers for the whole loop:
+//   e  = 1 + dt*b_pml          f = dt*rho*b0          cl = c_lin          g = rho*c_nl
+// so that, with d = 1 + (u/uth)^2,
+//   q = 1/(1 + dt*b(u)) = 1/(e + f/d) = d/(d*e + f)          c(u) = cl + g*u^2          (cell.py:94-102, :12-17)
+// One MUFU reciprocal per cell and step in the forward kernel, two in the adjoint (which also needs 1/d).  rcp.approx is
+// within 1 ulp; q only scales the damping, the u_{t-1}/u_{t-2} weights a1 and 1-a1 still sum to exactly one.
 template <int R>
-__device__ __forceinline__ void load_fields3(const ResArgs& a, bool active, int gi0, int j0, float (&bp)[R][4],
-                                             float (&cl)[R][4], float (&rh)[R][4]) {
+__device__ __forceinline__ void load_nl_consts(const ResArgs& a, bool active, int gi0, int j0, float (&e)[R][4],
+                                               float (&f)[R][4], float (&cl)[R][4], float (&g)[R][4]) {
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -27,10 +33,19 @@ __device__ __forceinline__ void load_fields3(const ResArgs& a, bool active, int 
       bool ok = active && gi < a.Nx && j < a.Ny;
       size_t o = (size_t)gi * a.Ny + j;
       // cells outside the domain: c = 0 makes a3 = 0, so they stay exactly zero like the linear kernels' padding
-      bp[r][k] = ok ? a.bpml[o] : 0.f;
+      const float bp = ok ? a.bpml[o] : 0.f;
+      const float rh = ok ? a.rho[o] : 0.f;
+      e[r][k] = fmaf(bp, a.s.dt, 1.f);
+      f[r][k] = a.s.dt * (rh * a.s.b0);
       cl[r][k] = ok ? a.clin[o] : 0.f;
-      rh[r][k] = ok ? a.rho[o] : 0.f;
+      g[r][k] = rh * a.s.c_nl;
     }
+}
+
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // =================================================================================================
@@ -49,8 +64,20 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
   Lane<R> L;
   L.init(a, fld, bars);
   const int tid = L.tid, NT = blockDim.x;
-  float bp[R][4], cl[R][4], rh[R][4];
-  load_fields3<R>(a, L.active, L.gi0, L.j0, bp, cl, rh);
+  float ce[R][4], cf[R][4], cl[R][4], cg[R][4];
+  load_nl_consts<R>(a, L.active, L.gi0, L.j0, ce, cf, cl, cg);
+  if (!KERR) {   // constant wave speed: keep kappa*c^2
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) cl[r][k] = a.s.kappa * (cl[r][k] * cl[r][k]);
+  }
+  if (!SAT) {    // constant damping: keep q
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ce[r][k] = __frcp_rn(ce[r][k]);
+  }
   unsigned m1, m2;
   source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
@@ -118,10 +145,19 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            float bb, cc, d;
-            wt_nl_bc<SAT, KERR>(s, bp[r][k], cl[r][k], rh[r][k], cu[r][k], bb, cc, d);
-            const CellCoef kc = wt_coef(s, bb, cc);
-            pr[r][k] = wt_update(kc.a1, kc.a3, cu[r][k], pr[r][k], lap[r][k]);
+            const float u = cu[r][k];
+            float q = ce[r][k];              // !SAT: 1/(1 + dt*b_pml)
+            if (SAT) {
+              const float rr = u * s.inv_uth;
+              const float d = fmaf(rr, rr, 1.f);
+              q = d * rcp_fast(fmaf(d, ce[r][k], cf[r][k]));
+            }
+            float kc2 = cl[r][k];            // !KERR: kappa*c_lin^2
+            if (KERR) {
+              const float cc = fmaf(cg[r][k], u * u, cl[r][k]);
+              kc2 = s.kappa * (cc * cc);
+            }
+            pr[r][k] = wt_update(q + q, q * kc2, u, pr[r][k], lap[r][k]);
           }
         if (m1) {
           const float xv = xs[(blk & 1) * TB + tt];
@@ -217,8 +253,8 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
   Lane<R> L;
   L.init(a, fld, bars);
   const int tid = L.tid;
-  float bp[R][4], cl[R][4], rh[R][4];
-  load_fields3<R>(a, L.active, L.gi0, L.j0, bp, cl, rh);
+  float ce[R][4], cf[R][4], cl[R][4], cg[R][4];
+  load_nl_consts<R>(a, L.active, L.gi0, L.j0, ce, cf, cl, cg);
   unsigned m1, m2;
   source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
@@ -242,6 +278,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
     }
   const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
   const Scalars s = a.s;
+  const float ndtb0 = -s.dt * s.b0, two_iu2 = 2.f * s.inv_uth * s.inv_uth;
 
   float Gc[R][4], Gr[R][4];
 #pragma unroll
@@ -344,29 +381,34 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float u1 = u1a[k], u2 = u2a[k];
-            float bb, cc, d;
-            wt_nl_bc<SAT, KERR>(s, bp[r][k], cl[r][k], rh[r][k], u1, bb, cc, d);
-            const float beta = bb * s.dt;
-            const float q = __frcp_rn(1.f + beta);
+            // coefficients at u_{t-1}: q = 1/(1+dt*b), c, and rd = 1/d of the saturable term
+            float rd = 1.f, den = ce[r][k], cc = cl[r][k];
+            if (SAT) {
+              const float rr = u1 * s.inv_uth;
+              rd = rcp_fast(fmaf(rr, rr, 1.f));
+              den = fmaf(cf[r][k], rd, ce[r][k]);               // 1 + dt*b(u)
+            }
+            const float uu = u1 * u1;
+            if (KERR) cc = fmaf(cg[r][k], uu, cl[r][k]);
+            const float q = rcp_fast(den);
             const float ql = q * lam[r][k];
             const float kl = s.kappa * lpa[k];
-            const float S = fmaf(cc * cc, kl, 2.f * (u1 - u2));
-            const float g_b = -s.dt * q * S * ql;            // cell.py:33-34
-            const float g_c = 2.f * cc * kl * ql;             // cell.py:36
-            float gu1 = 2.f * ql;                             // own-cell part of cell.py:39-40
-            if (SAT) {
-              const float iu = s.inv_uth;
-              const float rd = __frcp_rn(d);
-              Gr[r][k] = fmaf(g_b, s.b0 * rd, Gr[r][k]);
-              gu1 = fmaf(g_b, rh[r][k] * s.b0 * (-2.f * u1 * iu * iu) * (rd * rd), gu1);
+            const float cc2 = cc * cc;
+            const float S = fmaf(cc2, kl, 2.f * (u1 - u2));
+            const float g_c = (cc + cc) * (kl * ql);            // cell.py:36
+            float gu1 = ql + ql;                                // own-cell part of cell.py:39-40
+            if (SAT) {   // dLoss/db = -dt*q*S*ql (cell.py:33-34) through b = b_pml + rho*b0/d
+              const float X = (q * S) * (ql * rd);              // -dLoss/db / (dt*d)
+              Gr[r][k] = fmaf(X, ndtb0, Gr[r][k]);              // d b/d rho = b0/d
+              gu1 = fmaf((X * rd) * cf[r][k], two_iu2 * u1, gu1);   // d b/d u = -2*rho*b0*u/(uth^2 d^2)
             }
             if (KERR) {
-              Gr[r][k] = fmaf(g_c, s.c_nl * u1 * u1, Gr[r][k]);
-              gu1 = fmaf(g_c, 2.f * rh[r][k] * s.c_nl * u1, gu1);
+              Gr[r][k] = fmaf(g_c, s.c_nl * uu, Gr[r][k]);
+              gu1 = fmaf(g_c, (cg[r][k] + cg[r][k]) * u1, gu1);
             }
             Gc[r][k] += g_c;
-            pv[r][k] = s.kappa * cc * cc * ql;
-            g2[r][k] = (beta - 1.f) * ql;                     // cell.py:42
+            pv[r][k] = (s.kappa * cc2) * ql;
+            g2[r][k] = (den - 2.f) * ql;                        // (beta-1)*q*lambda, cell.py:42
             lam[r][k] = c2[r][k] + gu1;                       // everything of lambda_{t-1} except the stencil term
           }
         }
