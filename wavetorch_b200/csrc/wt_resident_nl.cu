@@ -13,7 +13,7 @@ namespace wt {
 
 template <int R>
 constexpr int res_nl_max_threads() {
-  return R <= 2 ? 512 : R == 3 ? 448 : 384;   // register budget: the nonlinear adjoint keeps ~9 values per cell live
+  return R <= 2 ? 512 : R == 3 ? 384 : 384;   // register budget: the nonlinear adjoint keeps ~9 values per cell live
 }
 
 // Per-cell constants of the nonlinear coefficients, kept in registers for the whole loop:
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
       const unsigned gi = it_global + it;
       const unsigned slot = gi % RG, parity = (gi / RG) & 1u;
       const unsigned slot2 = (gi + 1) % RG, parity2 = ((gi + 1) / RG) & 1u;   // stage of step t-1: its u is my u_{t-2}
-      float pv[R][4], g2[R][4];   // across the barrier: P (stencil centre), the new carry; lam holds c2 + own-cell part
+      float pv[R][4];   // across the barrier: P (stencil centre); lam holds the old carry + own-cell part, c2 the new carry
       if (L.active) {
         if (pc0 >= 0) {   // lambda_t += dLoss/du_t through the probes (first probe of my patch: fast path)
           const float* srow = ss + (blk & 1) * TB * a.n_prb + tt * a.n_prb;
@@ -408,8 +408,8 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
             }
             Gc[r][k] += g_c;
             pv[r][k] = (s.kappa * cc2) * ql;
-            g2[r][k] = (den - 2.f) * ql;                        // (beta-1)*q*lambda, cell.py:42
             lam[r][k] = c2[r][k] + gu1;                       // everything of lambda_{t-1} except the stencil term
+            c2[r][k] = (den - 2.f) * ql;                        // new carry (beta-1)*q*lambda, cell.py:42
           }
         }
         L.publish(a, fld, it & 1, pv);
@@ -427,10 +427,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            lam[r][k] += lapP[r][k];
-            c2[r][k] = g2[r][k];
-          }
+          for (int k = 0; k < 4; ++k) lam[r][k] += lapP[r][k];
       }
     }
     it_global += (unsigned)a.T;
@@ -460,7 +457,7 @@ int res_nl_max_threads_rt(int R) {
   switch (R) {
     case 1: return 512;
     case 2: return 512;
-    case 3: return 448;
+    case 3: return 384;
     case 4: return 384;
     default: return 0;
   }
