@@ -10,6 +10,8 @@
 //
 // HBM traffic per cell update: (2*E/O + 2)*4/K bytes for the fields (E/O = extended/owned cell ratio) instead of 12,
 // plus 4 for the tape when a gradient is wanted.  Coefficients are loaded once per tile and reused for every sample.
+#include <type_traits>
+
 #include "wt_common.cuh"
 #include "wt_stream.h"
 #include "wt_tile.h"
@@ -43,7 +45,7 @@ struct TileArgs {
 };
 
 constexpr int TILE_MAX_PRB = 32;
-constexpr int TILE_MAX_K = 8;
+constexpr int TILE_MAX_K = 4;    // steps per launch: the step bodies are unrolled with a compile-time step index
 constexpr int TILE_ADJ_K = 4;   // the adjoint keeps K steps of tape staged per thread: fixed depth
 
 // Ampere-style asynchronous copies: every thread stages ITS OWN patch of the next sample (and, in the adjoint, its tape
@@ -60,6 +62,27 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Unscaled 5-point Laplacian of a thread's R x 4 patch: own cells from registers, the rim from the slab buffer
+template <int R>
+__device__ __forceinline__ void patch_lap(int pitch, const float* ownp, const float (&cu)[R][4], float (&lap)[R][4]) {
+  const float4 up = *reinterpret_cast<const float4*>(ownp - pitch);
+  const float4 dn = *reinterpret_cast<const float4*>(ownp + R * pitch);
+  const float upv[4] = {up.x, up.y, up.z, up.w};
+  const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float lf = ownp[r * pitch - 1], rt = ownp[r * pitch + 4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float n = (r == 0) ? upv[k] : cu[r - 1][k];
+      const float s = (r == R - 1) ? dnv[k] : cu[r + 1][k];
+      const float wv = (k == 0) ? lf : cu[r][k - 1];
+      const float e = (k == 3) ? rt : cu[r][k + 1];
+      lap[r][k] = fmaf(-4.f, cu[r][k], (n + s) + (wv + e));
+    }
+  }
+}
 
 // a1/a3 of a thread's patch (zero outside the domain)
 template <int R>
@@ -148,7 +171,11 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
   const bool row_mine[2] = {true, true};
   (void)row_mine;
   // which of my cells belong to the owned tile (the ones written back)
-  const bool col_in = (4 * g >= a.K) && (4 * g < a.K + a.TW) && (gj0 < a.Ny);
+  const bool col_in = active && (4 * g >= a.K) && (4 * g < a.K + a.TW) && (gj0 < a.Ny);
+  bool own_row[R];                                      // rows of my patch that belong to the tile itself
+#pragma unroll
+  for (int r = 0; r < R; ++r) own_row[r] = col_in && lr0 + r >= a.K && lr0 + r < a.K + a.TH && gi0 + r < a.Nx;
+  const long long row0 = (long long)gi0 * a.Ny + gj0;   // my first row inside a [Nx,Ny] plane (only used where own_row)
 
   for (int b = b_lo; b < b_hi; ++b) {
     float v[R][4], w[R][4];
@@ -168,34 +195,21 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
     }
     __syncthreads();
 
-    auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int j) {
-      const float* cur = fld + (j & 1) * slab;
-      float* nxt = fld + ((j + 1) & 1) * slab;
+    // One step; J (the step inside the block) is a compile-time constant of each unrolled copy, so buffer parity and the
+    // x slot are immediates.  `cu` = u_t (kept), `pr` = u_{t-1} on entry and u_{t+1} on exit.
+    auto step = [&](auto jc, float (&cu)[R][4], float (&pr)[R][4]) {
+      constexpr int J = decltype(jc)::value;
+      const float* cur = fld + (J & 1) * slab;
+      float* nxt = fld + ((J + 1) & 1) * slab;
       if (active) {
-        const float* ownp = cur + own;
-        const float4 up = *reinterpret_cast<const float4*>(ownp - a.pitch);
-        const float4 dn = *reinterpret_cast<const float4*>(ownp + R * a.pitch);
-        const float upv[4] = {up.x, up.y, up.z, up.w};
-        const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
         float lap[R][4];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float lf = ownp[r * a.pitch - 1], rt = ownp[r * a.pitch + 4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float n = (r == 0) ? upv[k] : cu[r - 1][k];
-            const float s = (r == R - 1) ? dnv[k] : cu[r + 1][k];
-            const float wv = (k == 0) ? lf : cu[r][k - 1];
-            const float e = (k == 3) ? rt : cu[r][k + 1];
-            lap[r][k] = fmaf(-4.f, cu[r][k], (n + s) + (wv + e));
-          }
-        }
+        patch_lap<R>(a.pitch, cur + own, cu, lap);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         if (m1) {
-          const float xv = xsb[j];
+          const float xv = xsb[J];
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -207,44 +221,44 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          *reinterpret_cast<float4*>(nxt + (lr0 + r + 1) * a.pitch + 4 + 4 * g) = make_float4(pr[r][0], pr[r][1], pr[r][2], pr[r][3]);
+          *reinterpret_cast<float4*>(nxt + own + r * a.pitch) = make_float4(pr[r][0], pr[r][1], pr[r][2], pr[r][3]);
         if (a.tape && col_in) {
-          float* tp = a.tape + ((size_t)(a.t0 + j) * a.B + b) * plane;
+          float* tp = a.tape + ((size_t)(a.t0 + J) * a.B + b) * plane + row0;
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int gi = gi0 + r, li = lr0 + r;
-            if (li >= a.K && li < a.K + a.TH && gi < a.Nx)
-              *reinterpret_cast<float4*>(tp + (size_t)gi * a.Ny + gj0) = make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]);
-          }
+          for (int r = 0; r < R; ++r)
+            if (own_row[r]) *reinterpret_cast<float4*>(tp + r * a.Ny) = make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]);
         }
       }
       __syncthreads();
       if (tid < n_my_prb) {   // probe.py:15/27 on the field that now sits in `nxt`
         const float val = nxt[poff[tid]];
-        const size_t o = ((size_t)b * a.T + a.t0 + j) * a.n_prb + pid[tid];
+        const size_t o = ((size_t)b * a.T + a.t0 + J) * a.n_prb + pid[tid];
         if (a.probe_raw) a.probe_raw[o] = val;
         if (a.probe_out) a.probe_out[o] = a.prb_sq[pid[tid]] ? val * val : val;
       }
     };
-    int j = 0;
-    for (; j + 1 < a.steps; j += 2) {
-      step(v, w, j);
-      step(w, v, j + 1);
-    }
-    bool latest_in_v = true;
-    if (j < a.steps) { step(v, w, j); latest_in_v = false; }
+    auto body = [&](auto jc) {
+      constexpr int J = decltype(jc)::value;
+      if (J < a.steps) {
+        if (J & 1) step(jc, w, v); else step(jc, v, w);
+      }
+    };
+    body(std::integral_constant<int, 0>{});
+    body(std::integral_constant<int, 1>{});
+    body(std::integral_constant<int, 2>{});
+    body(std::integral_constant<int, 3>{});
+    const bool latest_in_v = (a.steps & 1) == 0;
     // write the owned tile back (latest -> V1, previous -> V2)
-    if (active && col_in) {
-      float* o1 = a.V1 + (size_t)b * plane;
-      float* o2 = a.V2 + (size_t)b * plane;
+    if (col_in) {
+      float* o1 = a.V1 + (size_t)b * plane + row0;
+      float* o2 = a.V2 + (size_t)b * plane + row0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int gi = gi0 + r, li = lr0 + r;
-        if (li >= a.K && li < a.K + a.TH && gi < a.Nx) {
+        if (own_row[r]) {
           const float4 hi = latest_in_v ? make_float4(v[r][0], v[r][1], v[r][2], v[r][3]) : make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
           const float4 lo = latest_in_v ? make_float4(w[r][0], w[r][1], w[r][2], w[r][3]) : make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-          *reinterpret_cast<float4*>(o1 + (size_t)gi * a.Ny + gj0) = hi;
-          *reinterpret_cast<float4*>(o2 + (size_t)gi * a.Ny + gj0) = lo;
+          *reinterpret_cast<float4*>(o1 + r * a.Ny) = hi;
+          *reinterpret_cast<float4*>(o2 + r * a.Ny) = lo;
         }
       }
     }
@@ -297,6 +311,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
   bool own_row[R];                                      // rows of my patch that belong to the tile itself
 #pragma unroll
   for (int r = 0; r < R; ++r) own_row[r] = col_in && lr0 + r >= a.K && lr0 + r < a.K + a.TH && gi0 + r < a.Nx;
+  const long long row0 = (long long)gi0 * a.Ny + gj0;   // my first row inside a [Nx,Ny] plane (only used where own_row)
 
   // copy group j of sample b: the tape rows of reverse step j, plus (j == 0) the two state patches.  Exactly TILE_ADJ_K
   // groups are committed per sample, empty ones included, so that "at most K-1 groups pending" always means "the oldest
@@ -319,7 +334,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
         const float* tb = a.tape + ((size_t)(a.t0 - j) * a.B + b) * plane;
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          cp_async16(&ring[(j * R + r) * NT + tid], tb + (own_row[r] ? (size_t)(gi0 + r) * a.Ny + gj0 : 0), own_row[r]);
+          cp_async16(&ring[(j * R + r) * NT + tid], own_row[r] ? tb + row0 + r * a.Ny : tb, own_row[r]);
       }
     }
     cp_async_commit();
@@ -386,57 +401,51 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
     }
     __syncthreads();
 
-    // one reverse step: cu = P_t (kept), pr = P_{t+1} (or the weighted carry) on entry and P_{t-1} on exit
-    auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int j) {
-      const int t = a.t0 - j;
-      const float* cur = fld + (j & 1) * slab;
-      float* nxt = fld + ((j + 1) & 1) * slab;
+    // One reverse step; J (the step inside the block) is a compile-time constant of each unrolled copy: buffer parity and
+    // ring slots are immediates.  cu = P_t (kept), pr = P_{t+1} (or the weighted carry) on entry and P_{t-1} on exit.
+    auto step = [&](auto jc, float (&cu)[R][4], float (&pr)[R][4]) {
+      constexpr int J = decltype(jc)::value;
+      const int t = a.t0 - J;
+      const float* cur = fld + (J & 1) * slab;
+      float* nxt = fld + ((J + 1) & 1) * slab;
+      if (m1) {   // dLoss/dx[b,t] = sum over source pixels of lambda_t = P_t / a3
+        float sx = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (m1 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
+            if (m2 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
+            if (m3 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
+          }
+        atomicAdd(aa.grad_x + (size_t)b * a.T + t, sx);
+      }
+      if (J > 0) cp_async_wait<TILE_ADJ_K - 1>();   // tape rows of this step
+      if (col_in) {
+        const float4* rs = ring + J * R * NT + tid;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 tp = rs[r * NT];   // zero-filled where the row is not mine
+          G[r][0] = fmaf(tp.x, cu[r][0], G[r][0]);
+          G[r][1] = fmaf(tp.y, cu[r][1], G[r][1]);
+          G[r][2] = fmaf(tp.z, cu[r][2], G[r][2]);
+          G[r][3] = fmaf(tp.w, cu[r][3], G[r][3]);
+        }
+      }
+      stage(b + 1, J);   // refill the slots just consumed with the next sample's
       if (active) {
-        if (m1) {   // dLoss/dx[b,t] = sum over source pixels of lambda_t = P_t / a3
-          float sx = 0.f;
+        float lap[R][4];
+        patch_lap<R>(a.pitch, cur + own, cu, lap);
+        if (J == 0 && aa.premul_first) {   // the carry is already weighted by (1 - a1)
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (m1 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
-              if (m2 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
-              if (m3 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
-            }
-          atomicAdd(aa.grad_x + (size_t)b * a.T + t, sx);
-        }
-        if (j > 0) cp_async_wait<TILE_ADJ_K - 1>();   // tape rows of this step
-        if (col_in) {
+            for (int k = 0; k < 4; ++k) pr[r][k] = fmaf(k3[r][k], lap[r][k], fmaf(k1[r][k], cu[r][k], pr[r][k]));
+        } else {
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const float4 tp = ring[(j * R + r) * NT + tid];   // zero-filled where the row is not mine
-            G[r][0] = fmaf(tp.x, cu[r][0], G[r][0]);
-            G[r][1] = fmaf(tp.y, cu[r][1], G[r][1]);
-            G[r][2] = fmaf(tp.z, cu[r][2], G[r][2]);
-            G[r][3] = fmaf(tp.w, cu[r][3], G[r][3]);
-          }
-        }
-      }
-      stage(b + 1, j);   // refill the slots just consumed with the next sample's
-      if (active) {
-        const float* ownp = cur + own;
-        const float4 up = *reinterpret_cast<const float4*>(ownp - a.pitch);
-        const float4 dn = *reinterpret_cast<const float4*>(ownp + R * a.pitch);
-        const float upv[4] = {up.x, up.y, up.z, up.w};
-        const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
-        const bool premul = aa.premul_first && j == 0;
+          for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float lf = ownp[r * a.pitch - 1], rt = ownp[r * a.pitch + 4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float n = (r == 0) ? upv[k] : cu[r - 1][k];
-            const float s = (r == R - 1) ? dnv[k] : cu[r + 1][k];
-            const float wv = (k == 0) ? lf : cu[r][k - 1];
-            const float e = (k == 3) ? rt : cu[r][k + 1];
-            const float lap = fmaf(-4.f, cu[r][k], (n + s) + (wv + e));
-            pr[r][k] = premul ? fmaf(k3[r][k], lap, fmaf(k1[r][k], cu[r][k], pr[r][k]))
-                              : wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap);
-          }
+            for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         }
         if (my_np && t > 0) {   // P_{t-1} += a3 * seed_{t-1}
           for (int p = 0; p < n_my_prb; ++p)
@@ -454,25 +463,30 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          *reinterpret_cast<float4*>(nxt + (lr0 + r + 1) * a.pitch + 4 + 4 * g) = make_float4(pr[r][0], pr[r][1], pr[r][2], pr[r][3]);
+          *reinterpret_cast<float4*>(nxt + own + r * a.pitch) = make_float4(pr[r][0], pr[r][1], pr[r][2], pr[r][3]);
       }
       __syncthreads();
     };
-    int j = 0;
-    for (; j + 1 < a.steps; j += 2) {
-      step(v, w, j);
-      step(w, v, j + 1);
-    }
-    bool latest_in_v = true;
-    if (j < a.steps) { step(v, w, j); latest_in_v = false; ++j; }
-    for (; j < TILE_ADJ_K; ++j) stage(b + 1, j);   // short last block: keep the group count per sample fixed
+    auto body = [&](auto jc) {
+      constexpr int J = decltype(jc)::value;
+      if (J < a.steps) {
+        if (J & 1) step(jc, w, v); else step(jc, v, w);
+      } else {
+        stage(b + 1, J);   // short last block: keep the group count per sample fixed
+      }
+    };
+    body(std::integral_constant<int, 0>{});
+    body(std::integral_constant<int, 1>{});
+    body(std::integral_constant<int, 2>{});
+    body(std::integral_constant<int, 3>{});
+    static_assert(TILE_ADJ_K == 4, "the reverse steps are unrolled four times");
+    const bool latest_in_v = (a.steps & 1) == 0;
     if (col_in) {   // owned tile back to HBM: V1 = P_{t_hi-steps}, V2 = P_{t_hi-steps+1}
-      float* o1 = a.V1 + (size_t)b * plane;
-      float* o2 = a.V2 + (size_t)b * plane;
+      float* o1 = a.V1 + (size_t)b * plane + row0;
+      float* o2 = a.V2 + (size_t)b * plane + row0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (own_row[r]) {
-          const int gi = gi0 + r;
           float4 hi = latest_in_v ? make_float4(v[r][0], v[r][1], v[r][2], v[r][3]) : make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
           float4 lo = latest_in_v ? make_float4(w[r][0], w[r][1], w[r][2], w[r][3]) : make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
           if (aa.out_lambda) {
@@ -480,8 +494,8 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
             lo.x = (1.f - k1[r][0]) * lo.x / k3[r][0]; lo.y = (1.f - k1[r][1]) * lo.y / k3[r][1];
             lo.z = (1.f - k1[r][2]) * lo.z / k3[r][2]; lo.w = (1.f - k1[r][3]) * lo.w / k3[r][3];
           }
-          *reinterpret_cast<float4*>(o1 + (size_t)gi * a.Ny + gj0) = hi;
-          *reinterpret_cast<float4*>(o2 + (size_t)gi * a.Ny + gj0) = lo;
+          *reinterpret_cast<float4*>(o1 + r * a.Ny) = hi;
+          *reinterpret_cast<float4*>(o2 + r * a.Ny) = lo;
         }
       }
     }
@@ -543,9 +557,7 @@ struct TileGeom { int K, R, TH, TW, EH, EW, P4, pitch, runs, nact, threads, tile
 
 static TileGeom tile_geom(const wt_problem* p, int force_K = 0) {
   TileGeom t;
-  const char* ek = getenv("WT_TILE_K");
-  t.K = ek ? atoi(ek) : 4;
-  if (t.K != 8) t.K = 4;
+  t.K = TILE_MAX_K;   // K = 8 was measured slower (more halo work per useful cell)
   if (force_K) t.K = force_K;
   t.R = 4;
   const char* er = getenv("WT_TILE_R");
