@@ -249,8 +249,60 @@ def state_dict_case(name):
     print(name, keys)
 
 
+def train_case(name):
+    """wavetorch.train (train.py:13-133) for 2 epochs on a small deterministic problem, plus the checkpoint written by
+    io.save_model (io.py:13-41): loss / accuracy history and the final rho.  pandas >= 2 removed DataFrame.append, which
+    train.py:116 still calls; the shim below restores exactly that method for this run, nothing else is touched."""
+    import tempfile
+    import pandas as pd
+    from torch.utils.data import TensorDataset, DataLoader
+    if not hasattr(pd.DataFrame, "append"):
+        def _append(self, row, ignore_index=True):
+            return pd.concat([self, pd.DataFrame([row])], ignore_index=True)
+        pd.DataFrame.append = _append
+    _dtype("float32")
+    torch.manual_seed(0)
+    Nx, Ny, N, T, n_train, n_test, bs = 44, 36, 5, 80, 9, 6, 3
+    design_region = torch.zeros(Nx, Ny, dtype=torch.uint8)
+    design_region[14:30] = 1
+    geom = wt.WaveGeometryFreeForm((Nx, Ny), 1.0, c0=1.0, c1=0.6, eta=0.5, beta=100, abs_sig=3.0, abs_N=N, abs_p=4.0,
+                                   rho="half", blur_radius=1, blur_N=1, design_region=design_region)
+    cell = wt.WaveCell(0.6, geom)
+    probes = [wt.WaveIntensityProbe(36, y) for y in (10, 18, 26)]
+    model = wt.WaveRNN(cell, [wt.WaveSource(8, 18)], probes)
+    Xall = torch.tensor(wo.synthetic_vowels(n_train + n_test, T, dtype=np.float64), dtype=torch.float32)
+    lab = torch.arange(n_train + n_test) % 3
+    Yall = torch.nn.functional.one_hot(lab, 3).to(torch.float32)
+    train_dl = DataLoader(TensorDataset(Xall[:n_train], Yall[:n_train]), batch_size=bs, shuffle=False)
+    test_dl = DataLoader(TensorDataset(Xall[n_train:], Yall[n_train:]), batch_size=bs)
+    optimizer = torch.optim.Adam(model.parameters(), lr=0.02)
+    rho0 = _np(geom.rho).copy()
+    cfg = {"dtype": "float32"}
+    with tempfile.TemporaryDirectory() as d:
+        history, states = wt.train(model, optimizer, torch.nn.CrossEntropyLoss(), train_dl, test_dl, 2, bs,
+                                   name="ck", savedir=d + "/", cfg=cfg, accuracy=wt.utils.accuracy_onehot)
+        data = torch.load(d + "/ck.pt", weights_only=False)
+    res = {"x": _np(Xall), "labels": lab.numpy(), "rho0": rho0, "rho_final": _np(geom.rho),
+           "design_region": _np(design_region),
+           "loss_train": history["loss_train"].to_numpy(dtype=np.float64),
+           "loss_test": history["loss_test"].to_numpy(dtype=np.float64),
+           "acc_train": history["acc_train"].to_numpy(dtype=np.float64),
+           "acc_test": history["acc_test"].to_numpy(dtype=np.float64),
+           "cm_train_last": np.asarray(history["cm_train"].iloc[-1]), "cm_test_last": np.asarray(history["cm_test"].iloc[-1]),
+           "epochs": history["epoch"].to_numpy(dtype=np.int64),
+           "ckpt_keys": np.array(sorted(data.keys())), "ckpt_state_keys": np.array(sorted(data["model_state"].keys())),
+           "ckpt_geom_class": np.array(data["model_geom_class_str"]),
+           "ckpt_geom_args": np.array(sorted(data["history_geom_state"][-1].keys())),
+           "n_states": np.asarray(len(states))}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **res)
+    print(name, res["loss_train"], res["loss_test"], res["acc_train"], res["acc_test"], res["ckpt_keys"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "train":      # regenerate only the training-loop fixture
+        train_case("train_small")
+        sys.exit(0)
     single_step_case("single_step")
     geometry_case("geometry")
     state_dict_case("state_dict")
@@ -265,3 +317,4 @@ if __name__ == "__main__":
     vowel_case("vowel_both", 6, 1000, 0.1, 1.0, -30.0)       # config 4 (ii)
     vowel_case("vowel_satdamp_uth", 6, 1000, 0.1, 0.00018, 0.0)  # config 4 (iii)
     vowel_case("vowel_kerr", 6, 1000, 0.0, 1.0, -30.0)
+    train_case("train_small")

@@ -135,3 +135,32 @@ def test_source_and_probe_modules_standalone_on_cpu():
     assert abs(wt.utils.normalize_power(torch.rand(4, 3)).sum(1) - 1).max() < 1e-6
     assert wt.utils.accuracy_onehot(torch.tensor([[0.1, 0.9], [0.8, 0.2]]), torch.tensor([1, 1])) == 0.5
     assert len(wt.utils.window_data(np.arange(100), 10)) == 10
+
+
+def test_confusion_matrix_matches_sklearn():
+    """wavetorch_b200.train.confusion_matrix replaces sklearn.metrics.confusion_matrix as called at train.py:93,106."""
+    from sklearn.metrics import confusion_matrix as sk_cm
+    from wavetorch_b200.train import confusion_matrix
+    rng = np.random.RandomState(0)
+    for labels in ([0, 1, 2], [0, 2], [1], [0, 1, 2, 5]):
+        yt = rng.choice(labels, size=40)
+        yp = rng.choice(labels, size=40)
+        np.testing.assert_array_equal(confusion_matrix(torch.tensor(yt), torch.tensor(yp)), sk_cm(yt, yp))
+
+
+def test_checkpoint_schema_round_trip(tmp_path):
+    """io.save_model / load_model keep the reference's .pt schema (io.py:28-36) and rebuild the same geometry; a
+    checkpoint written in the reference's layout (fixture key list) loads."""
+    g = load_golden("train_small")
+    geom = wt.WaveGeometryFreeForm((44, 36), 1.0, c0=1.0, c1=0.6, abs_N=5, rho="half", design_region=torch.tensor(g["design_region"]))
+    model = wt.WaveRNN(wt.WaveCell(0.6, geom), [wt.WaveSource(8, 18)], [wt.WaveIntensityProbe(36, y) for y in (10, 18, 26)])
+    wt.io.save_model(model, "m", str(tmp_path) + "/", cfg={"dtype": "float32"}, verbose=False)
+    data = torch.load(str(tmp_path) + "/m.pt", weights_only=False)
+    assert sorted(data.keys()) == list(g["ckpt_keys"])
+    assert sorted(data["model_state"].keys()) == list(g["ckpt_state_keys"])
+    m2, hist, states, cfg = wt.io.load_model(str(tmp_path) + "/m.pt", verbose=False)
+    assert hist is None and cfg == {"dtype": "float32"} and len(states) == 1
+    assert torch.equal(m2.cell.geom.rho.detach(), geom.rho.detach())
+    assert torch.equal(m2.cell.geom.b, geom.b)
+    assert [(int(p.x), int(p.y)) for p in m2.probes] == [(36, 10), (36, 18), (36, 26)]
+    assert (int(m2.sources[0].x), int(m2.sources[0].y)) == (8, 18)
