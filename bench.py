@@ -22,9 +22,9 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: NCCL's version banner and warnings (printed to stdout whenever NCCL_DEBUG is set)
+# go to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -368,7 +368,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config_dict(args, world), "clocks": clocks,
+        "data": "synthetic", "config": dict(config_dict(args, world), grad_allreduce=(
+            getattr(runner, "reduce_mode", "none") if world > 1 else "none")), "clocks": clocks,
         "e2e": {"value": world * cells_per_step / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + labels_host.numel() * 8), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "mode": mode},

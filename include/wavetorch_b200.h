@@ -186,6 +186,21 @@ int wt_loss_forward(int B, int T, int P, int B_total, const float* probe_out, co
 int wt_loss_backward(int B, int T, int P, const float* dlds, const float* grad_loss, float* grad_probe, int device,
                      void* stream);
 
+/*
+ * Sum-all-reduce of a small float vector across the GPUs of one box through NVLink peer memory, in one kernel launch:
+ * the collective of the batch-sharded path (dLoss/dc of every rank's waveforms), replacing ncclAllReduce for this message.
+ *   world, rank     ranks on this box (<= 16) and mine
+ *   src [n]         my contribution (multiplied by `scale` on the way out);  out [n]: the sum, bitwise identical on all ranks
+ *   peer_base       HOST array [world]: device address, valid in THIS process, of rank r's exchange buffer
+ *                   (cudaIpc / VMM mapped by the caller).  Layout of each buffer: float gather[2][world][nmax], then
+ *                   uint32 flags[world] at byte offset flags_offset_bytes; all zero before the first call
+ *   state           my own device uint32[2], zero before the first call (epoch, block counter)
+ * Every rank must call it the same number of times in the same order.  The kernel waits on the device for the peers; it
+ * is safe to capture in a CUDA graph.
+ */
+int wt_peer_allreduce(int world, int rank, int n, int nmax, float scale, const float* src, float* out,
+                      const uint64_t* peer_base, uint64_t flags_offset_bytes, uint32_t* state, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

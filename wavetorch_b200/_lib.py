@@ -19,7 +19,8 @@ WT_PATH_STREAM = 0
 WT_PATH_RESIDENT = 1
 
 EXPORTS = ("wt_abi_version", "wt_last_error", "wt_query_plan", "wt_forward", "wt_backward", "wt_step_forward",
-           "wt_step_backward", "wt_geom_forward", "wt_geom_backward", "wt_loss_forward", "wt_loss_backward")
+           "wt_step_backward", "wt_geom_forward", "wt_geom_backward", "wt_loss_forward", "wt_loss_backward",
+           "wt_peer_allreduce")
 
 
 class WtProblem(ctypes.Structure):
@@ -69,8 +70,11 @@ def load():
         lib.wt_geom_backward.argtypes = [i32, i32, i32, i32] + [vp] * 9 + [i32, vp]
         lib.wt_loss_forward.argtypes = [i32, i32, i32, i32] + [vp] * 6 + [i32, vp]
         lib.wt_loss_backward.argtypes = [i32, i32, i32] + [vp] * 3 + [i32, vp]
+        lib.wt_peer_allreduce.argtypes = [i32, i32, i32, i32, ctypes.c_float, vp, vp, ctypes.POINTER(ctypes.c_uint64),
+                                          ctypes.c_uint64, vp, i32, vp]
         for name in ("wt_query_plan", "wt_forward", "wt_backward", "wt_step_forward", "wt_step_backward",
-                     "wt_geom_forward", "wt_geom_backward", "wt_loss_forward", "wt_loss_backward"):
+                     "wt_geom_forward", "wt_geom_backward", "wt_loss_forward", "wt_loss_backward",
+                     "wt_peer_allreduce"):
             getattr(lib, name).restype = ctypes.c_int
         if lib.wt_abi_version() != 1:
             raise RuntimeError("wavetorch_b200: ABI version mismatch (library %d, binding 1)" % lib.wt_abi_version())
