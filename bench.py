@@ -24,6 +24,9 @@ import time
 
 # stdout carries exactly one JSON line: NCCL's version banner and warnings (printed to stdout whenever NCCL_DEBUG is set)
 # go to stderr instead
+# (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION is raised to WARN)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
