@@ -27,10 +27,13 @@ namespace wt {
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int R, bool TAPE>
+// PITCH / NTC: shared-memory row pitch and threads per CTA as compile-time constants (0 = take them from the launch).  The
+// BASELINE config-3 shape is instantiated with constants: every shared-memory and tape offset of the step becomes an immediate.
+template <int R, bool TAPE, int PITCH = 0, int NTC = 0>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
-  const int slab_f = (a.Hc + 2) * a.pitch;
+  const int pitch = PITCH ? PITCH : a.pitch;
+  const int slab_f = (a.Hc + 2) * pitch;
   float* fld = reinterpret_cast<float*>(smem4);       // [2][slab]
   float* xs = fld + 2 * slab_f;                        // [2][TB]
   float* ps = xs + 2 * TB;                             // [2][TB][n_prb]
@@ -39,19 +42,19 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 
   Lane<R> L;
   L.init(a, fld, bars);
-  const int tid = L.tid, NT = blockDim.x;
+  const int tid = L.tid, NT = NTC ? NTC : blockDim.x;
   float k1[R][4], k3[R][4];
   load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
   unsigned m1, m2;
   source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
-    poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * a.pitch + 4 + pj : -1;
+    poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * pitch + 4 + pj : -1;
   }
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
   const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
-  const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;     // my first row inside a slab buffer
+  const int own = (L.lr0 + 1) * pitch + 4 + L.j0;       // my first row inside a slab buffer
   const size_t tape_step = (size_t)a.C * R * NT;        // float4 per time step of one sample
   const size_t plane = (size_t)a.Nx * a.Ny;
 
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
         v[r][k] = ok ? a.u1[o] : 0.f;
         w[r][k] = ok ? a.u2[o] : 0.f;
       }
-    if (L.active) L.publish(a, fld, 0, v);
+    if (L.active) L.publish(pitch, fld, 0, v);
     ++L.npub;
     const float* xb = a.x + (size_t)b * a.T;
     for (int i = tid; i < TB && i < a.T; i += NT) xs[i] = xb[i];
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
       if (my_poff >= 0 && t > 0) psw[((t - 1) & (2 * TB - 1)) * a.n_prb] = (PAR ? fld + L.slab : fld)[my_poff];
       if (L.active) {
         float lap[R][4];
-        patch_laplacian<R>(a.pitch, cur, cu, lap);
+        patch_laplacian<R>(pitch, cur, cu, lap);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
               if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
             }
         }
-        L.publish(a, fld, PAR ^ 1, pr);
+        L.publish(pitch, fld, PAR ^ 1, pr);
         if (TAPE) {
 #pragma unroll
           for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
@@ -199,10 +202,11 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 // i.e. exactly the forward update (wt_update) run backwards in time, with the probe seeds playing the role of the
 // sources.  So this kernel is the forward kernel plus the tape: sum_t L(u_{t-1})*P_t accumulates per cell and
 // dLoss/dc = gscale * sum / a3 = (2/c) * sum  (cell.py:36).  dLoss/dx[b,t] = sum over source pixels of P_t/a3.
-template <int R>
+template <int R, int PITCH = 0, int NTC = 0>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
-  const int NT = blockDim.x;
-  const int slab_f = (a.Hc + 2) * a.pitch;
+  const int NT = NTC ? NTC : blockDim.x;
+  const int pitch = PITCH ? PITCH : a.pitch;
+  const int slab_f = (a.Hc + 2) * pitch;
   const unsigned stage_bytes = (unsigned)(R * NT * sizeof(float4));
 
   extern __shared__ float4 smem4[];
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     if (pown[p] == tid) {
       if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
     }
-  const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
+  const int own = (L.lr0 + 1) * pitch + 4 + L.j0;
   const size_t tape_step = (size_t)a.C * R * NT;
   // the lane that re-issues tape copies sits in a middle warp: the first and last warps already wait for ghost rows
   const int refill_tid = ((NT / 32) / 2) * 32;
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       for (int k = 0; k < 4; ++k) { v[r][k] = 0.f; w[r][k] = 0.f; }
     if (L.active) {
       add_seeds(v, a.T - 1);
-      L.publish(a, fld, 0, v);
+      L.publish(pitch, fld, 0, v);
     }
     ++L.npub;
     __syncthreads();
@@ -366,13 +370,13 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
         }
         if (t > 0) {
           float lap[R][4];
-          patch_laplacian<R>(a.pitch, cur, cu, lap);
+          patch_laplacian<R>(pitch, cur, cu, lap);
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
           add_seeds(pr, t - 1);
-          L.publish(a, fld, PAR ^ 1, pr);
+          L.publish(pitch, fld, PAR ^ 1, pr);
         }
       }
       if (t > 0) ++L.npub;
@@ -649,6 +653,12 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
   a.tape = reinterpret_cast<float4*>(history);
   a.status = status;
   if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st);
+  const char* esp = getenv("WT_RES_NOSPEC");
+  if (plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(esp && esp[0] == '1')) {   // BASELINE config 3
+    if (a.tape) WT_TRY(launch_cluster(k_res_fwd<5, true, 104, 384>, plan, plan.smem_fwd, a, st));
+    else WT_TRY(launch_cluster(k_res_fwd<5, false, 104, 384>, plan, plan.smem_fwd, a, st));
+    return WT_OK;
+  }
   if (a.tape) { WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, true>, plan, plan.smem_fwd, a, st))); }
   else { WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, false>, plan, plan.smem_fwd, a, st))); }
   return WT_OK;
@@ -686,7 +696,12 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
     WT_CUDA(cudaGetLastError());
     return WT_OK;
   }
-  WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st)));
+  const char* esp = getenv("WT_RES_NOSPEC");
+  if (plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(esp && esp[0] == '1')) {   // BASELINE config 3
+    WT_TRY(launch_cluster(k_res_adj<5, 104, 384>, plan, plan.smem_bwd, a, st));
+  } else {
+    WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st)));
+  }
   k_finish_grad_p<<<fg, 256, 0, st>>>(Gpart, c, plan.n_clusters, plane, plane, grad_c);
   if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
   if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));

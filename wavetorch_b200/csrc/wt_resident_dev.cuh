@@ -156,11 +156,12 @@ struct Lane {
   }
 
   // Write my R rows into slab buffer `which` (0/1) and push the rim rows to the neighbours.
-  __device__ __forceinline__ void publish(const ResArgs& a, float* fld, int which, const float (&v)[R][4]) {
-    float* buf = fld + which * slab;
+  // pitch: a.pitch, or the same value as a compile-time constant in the shape-specialised kernels
+  __device__ __forceinline__ void publish(int pitch, float* fld, int which, const float (&v)[R][4]) {
+    float* buf = fld + which * slab + (lr0 + 1) * pitch + 4 + j0;
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      *reinterpret_cast<float4*>(buf + (lr0 + r + 1) * a.pitch + 4 + j0) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+      *reinterpret_cast<float4*>(buf + r * pitch) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
     const uint32_t boff = (uint32_t)(which * slab) * 4u;
     const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
     if (edge_up) st_async_v4(push_up + boff, v[0][0], v[0][1], v[0][2], v[0][3], rbar_up + bsel);

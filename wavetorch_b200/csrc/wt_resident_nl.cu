@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
         v[r][k] = ok ? a.u1[o] : 0.f;
         w[r][k] = ok ? a.u2[o] : 0.f;
       }
-    if (L.active) L.publish(a, fld, 0, v);
+    if (L.active) L.publish(a.pitch, fld, 0, v);
     ++L.npub;
     const float* xb = a.x + (size_t)b * a.T;
     for (int i = tid; i < TB && i < a.T; i += NT) xs[i] = xb[i];
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
               if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
             }
         }
-        L.publish(a, fld, (t + 1) & 1, pr);
+        L.publish(a.pitch, fld, (t + 1) & 1, pr);
         if (fout) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
             c2[r][k] = (den - 2.f) * ql;                        // new carry (beta-1)*q*lambda, cell.py:42
           }
         }
-        L.publish(a, fld, it & 1, pv);
+        L.publish(a.pitch, fld, it & 1, pv);
       }
       ++L.npub;
       __syncthreads();
