@@ -348,14 +348,21 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       L.acquire_ghosts();
       if (L.active) {
         if (a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
+          // a loop over the (few) source cells of this thread with one division each: 4R unrolled divisions would
+          // triple the size of the step body for code that one thread per sample executes
           float s = 0.f;
+          for (unsigned mm = m1; mm; mm &= mm - 1u) {
+            const int bit = __ffs(mm) - 1;
+            float cv = 0.f, kv = 1.f;
 #pragma unroll
-          for (int r = 0; r < R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (m1 >> (r * 4 + k) & 1u) s += cu[r][k] / k3[r][k];
-              if (m2 >> (r * 4 + k) & 1u) s += cu[r][k] / k3[r][k];
-            }
+              for (int k = 0; k < 4; ++k)
+                if (bit == r * 4 + k) { cv = cu[r][k]; kv = k3[r][k]; }
+            const float q = cv / kv;
+            s += q;
+            if (m2 >> bit & 1u) s += q;
+          }
           atomicAdd(gxs + (t & (2 * TB - 1)), s);
         }
         mbar_wait(full + slot, parity);

@@ -408,16 +408,21 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
       const int t = a.t0 - J;
       const float* cur = fld + (J & 1) * slab;
       float* nxt = fld + ((J + 1) & 1) * slab;
-      if (m1) {   // dLoss/dx[b,t] = sum over source pixels of lambda_t = P_t / a3
+      if (m1) {   // dLoss/dx[b,t] = sum over source pixels of lambda_t = P_t / a3 (loop over my few source cells)
         float sx = 0.f;
+        for (unsigned mm = m1; mm; mm &= mm - 1u) {
+          const int bit = __ffs(mm) - 1;
+          float cv = 0.f, kv = 1.f;
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+          for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (m1 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
-            if (m2 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
-            if (m3 >> (r * 4 + k) & 1u) sx += cu[r][k] / k3[r][k];
-          }
+            for (int k = 0; k < 4; ++k)
+              if (bit == r * 4 + k) { cv = cu[r][k]; kv = k3[r][k]; }
+          const float q = cv / kv;
+          sx += q;
+          if (m2 >> bit & 1u) sx += q;
+          if (m3 >> bit & 1u) sx += q;
+        }
         atomicAdd(aa.grad_x + (size_t)b * a.T + t, sx);
       }
       if (J > 0) cp_async_wait<TILE_ADJ_K - 1>();   // tape rows of this step
