@@ -110,7 +110,8 @@ int wt_query_plan(const wt_problem* p, wt_plan* plan);
  *   u1, u2      [B,Nx,Ny] in: fields at t-1 and t-2 (ignored with WT_F_ZERO_INIT); out: the two latest fields
  *   probe_out   [B,T,n_prb] probe readout (squared where prb_square), the reference's model(x) output
  *   probe_raw   [B,T,n_prb] field at the probes (needed by wt_backward); may be NULL
- *   fields_out  [B,T,Nx,Ny] every field (output_fields=True, rnn.py:65-67); may be NULL
+ *   fields_out  [B,T,Nx,Ny] every field (output_fields=True, rnn.py:65-67); may be NULL.  Together with `history` it
+ *               needs WT_F_FORCE_STREAM (dLoss/dfields is implemented by the streaming adjoint); WT_EUNSUPPORTED otherwise
  *   history     adjoint tape of plan.history_bytes, or NULL for inference
  *   workspace   plan.workspace_fwd_bytes
  */

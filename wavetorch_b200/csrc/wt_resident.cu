@@ -29,7 +29,9 @@ namespace wt {
 // =================================================================================================
 // PITCH / NTC: shared-memory row pitch and threads per CTA as compile-time constants (0 = take them from the launch).  The
 // BASELINE config-3 shape is instantiated with constants: every shared-memory and tape offset of the step becomes an immediate.
-template <int R, bool TAPE, int PITCH = 0, int NTC = 0>
+// FIELDS: also write every field to HBM (output_fields=True); a separate instantiation keeps that code out of the step body
+// of the common kernels, which is fetched from the instruction cache 2T times per sample.
+template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
   const int pitch = PITCH ? PITCH : a.pitch;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
     __syncthreads();
 
     float4* tape = TAPE ? a.tape + (((size_t)b * a.T) * a.C + L.rank) * R * NT + tid : nullptr;
-    float* fout = a.fields ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
+    float* fout = FIELDS ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
 
     auto flush = [&](int blk) {   // probe samples of time block blk -> HBM
       const int t0 = blk * TB, n = min(TB, a.T - t0);
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
           for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
           tape += tape_step;
         }
-        if (fout) {
+        if (FIELDS) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (L.gi0 + r < a.Nx) {
@@ -661,9 +663,14 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
   a.status = status;
   if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st);
   const char* esp = getenv("WT_RES_NOSPEC");
-  if (plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(esp && esp[0] == '1')) {   // BASELINE config 3
+  if (!a.fields && plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(esp && esp[0] == '1')) {   // BASELINE config 3
     if (a.tape) WT_TRY(launch_cluster(k_res_fwd<5, true, 104, 384>, plan, plan.smem_fwd, a, st));
     else WT_TRY(launch_cluster(k_res_fwd<5, false, 104, 384>, plan, plan.smem_fwd, a, st));
+    return WT_OK;
+  }
+  if (a.fields) {
+    if (a.tape) { wt::set_error("wt_forward: fields_out together with history needs WT_F_FORCE_STREAM"); return WT_EUNSUPPORTED; }
+    WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, false, 0, 0, true>, plan, plan.smem_fwd, a, st)));
     return WT_OK;
   }
   if (a.tape) { WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, true>, plan, plan.smem_fwd, a, st))); }
