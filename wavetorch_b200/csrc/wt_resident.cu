@@ -519,7 +519,7 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
   const int* Rs = nl ? Rs_nl : Rs_lin;
   const int nR = nl ? 4 : 7;
   auto ring_for = [&](int Hc, int R, int threads) {   // deepest tape ring that fits (nonlinear stages are twice as big)
-    for (int ring = RING; ring >= 2; --ring)
+    for (int ring = RING; ring >= 2; ring /= 2)   // powers of two: slot and parity of a stage are a mask and a shift
       if ((int)res_nl_smem_adj(Hc, pitch, p->n_prb, R, threads, ring) <= smem_cap) return ring;
     return 0;
   };

@@ -51,7 +51,7 @@ __device__ __forceinline__ float rcp_fast(float x) {
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int R, bool SAT, bool KERR>
+template <int R, bool SAT, bool KERR, bool FIELDS = false>
 __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs a) {
   extern __shared__ float4 smem4[];
   const int slab_f = (a.Hc + 2) * a.pitch;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
     __syncthreads();
 
     float4* tape = a.tape ? a.tape + (((size_t)b * a.T) * a.C + L.rank) * 2 * R * NT + tid : nullptr;
-    float* fout = a.fields ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
+    float* fout = FIELDS ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
 
     auto flush = [&](int blk) {
       const int t0 = blk * TB, n = min(TB, a.T - t0);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
             }
         }
         L.publish(a.pitch, fld, (t + 1) & 1, pr);
-        if (fout) {
+        if (FIELDS) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (L.gi0 + r < a.Nx) {
@@ -236,7 +236,8 @@ template <int R, bool SAT, bool KERR>
 __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs a) {
   const int NT = blockDim.x;
   const int slab_f = (a.Hc + 2) * a.pitch;
-  const int RG = a.ring;
+  const int RG = a.ring;                        // 2 or 4 (resident_plan)
+  const unsigned rg_mask = (unsigned)RG - 1u, rg_shift = RG == 4 ? 2u : 1u;
   const int stage_f4 = 2 * R * NT;
   const unsigned stage_bytes = (unsigned)(stage_f4 * sizeof(float4));
 
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
     };
     if (tid == 0) {
       for (int q = 0; q < RG && q < a.T; ++q) {
-        unsigned slot = (it_global + q) % RG;
+        unsigned slot = (it_global + q) & rg_mask;
         mbar_expect_tx(full + slot, stage_bytes);
         bulk_g2s(ring + slot * stage_f4, tape_ptr(a.T - 1 - q), stage_bytes, full + slot);
       }
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
       if ((t == a.T - 1 || tt == TB - 1) && blk > 0) stage_seeds(blk - 1);
       if (a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
       const unsigned gi = it_global + it;
-      const unsigned slot = gi % RG, parity = (gi / RG) & 1u;
-      const unsigned slot2 = (gi + 1) % RG, parity2 = ((gi + 1) / RG) & 1u;   // stage of step t-1: its u is my u_{t-2}
+      const unsigned slot = gi & rg_mask, parity = (gi >> rg_shift) & 1u;
+      const unsigned slot2 = (gi + 1) & rg_mask, parity2 = ((gi + 1) >> rg_shift) & 1u;   // stage of step t-1: its u is my u_{t-2}
       float pv[R][4];   // across the barrier: P (stencil centre); lam holds the old carry + own-cell part, c2 the new carry
       if (L.active) {
         if (pc0 >= 0) {   // lambda_t += dLoss/du_t through the probes (first probe of my patch: fast path)
@@ -529,7 +530,11 @@ static int nl_launch(K kernel, const wt_plan& plan, size_t smem, const ResArgs& 
 int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
   const int R = plan.rows_per_thread, nl = plan.nonlinear;
   int rc = WT_EINVAL;
-  WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR>, plan, plan.smem_fwd, a, st)))
+  if (a.fields) {   // output_fields=True: separate instantiation, keeps the field stores out of the common step body
+    WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR, true>, plan, plan.smem_fwd, a, st)))
+  } else {
+    WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR>, plan, plan.smem_fwd, a, st)))
+  }
   if (rc == WT_EINVAL) set_error("nonlinear on-chip kernel R=%d nl=%d not instantiated", R, nl);
   return rc;
 }
