@@ -6,6 +6,8 @@
 //     step with the same device functions as the streaming path (wt_common.cuh), so both paths agree bitwise
 //   * the tape holds u_{t-1} AND L(u_{t-1}) per step (8 B/cell); u_{t-2} is read from the next ring stage
 //   * the adjoint accumulates dLoss/dc_lin and the direct dLoss/drho per cluster
+#include <type_traits>
+
 #include "wt_resident.h"
 #include "wt_resident_dev.cuh"
 
@@ -51,10 +53,11 @@ __device__ __forceinline__ float rcp_fast(float x) {
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int R, bool SAT, bool KERR, bool FIELDS = false>
-__global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs a) {
+template <int R, bool SAT, bool KERR, bool FIELDS = false, int PITCH = 0, int NTC = 0>
+__global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs a) {
   extern __shared__ float4 smem4[];
-  const int slab_f = (a.Hc + 2) * a.pitch;
+  const int pitch = PITCH ? PITCH : a.pitch;
+  const int slab_f = (a.Hc + 2) * pitch;
   float* fld = reinterpret_cast<float*>(smem4);
   float* xs = fld + 2 * slab_f;
   float* ps = xs + 2 * TB;
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
 
   Lane<R> L;
   L.init(a, fld, bars);
-  const int tid = L.tid, NT = blockDim.x;
+  const int tid = L.tid, NT = NTC ? NTC : blockDim.x;
   float ce[R][4], cf[R][4], cl[R][4], cg[R][4];
   load_nl_consts<R>(a, L.active, L.gi0, L.j0, ce, cf, cl, cg);
   if (!KERR) {   // constant wave speed: keep kappa*c^2
@@ -82,12 +85,12 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
   source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
-    poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * a.pitch + 4 + pj : -1;
+    poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * pitch + 4 + pj : -1;
   }
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
   const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
-  const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
+  const int own = (L.lr0 + 1) * pitch + 4 + L.j0;
   const size_t tape_step = (size_t)a.C * 2 * R * NT;
   const size_t plane = (size_t)a.Nx * a.Ny;
   const Scalars s = a.s;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
         v[r][k] = ok ? a.u1[o] : 0.f;
         w[r][k] = ok ? a.u2[o] : 0.f;
       }
-    if (L.active) L.publish(a.pitch, fld, 0, v);
+    if (L.active) L.publish(pitch, fld, 0, v);
     ++L.npub;
     const float* xb = a.x + (size_t)b * a.T;
     for (int i = tid; i < TB && i < a.T; i += NT) xs[i] = xb[i];
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
       if (t > 0 && my_poff >= 0) ps[(((t - 1) / TB) & 1) * TB * a.n_prb + ((t - 1) % TB) * a.n_prb + tid] = cur[my_poff];
       if (L.active) {
         float lap[R][4];
-        patch_laplacian<R>(a.pitch, cur + own, cu, lap);
+        patch_laplacian<R>(pitch, cur + own, cu, lap);
         if (tape) {   // the adjoint needs u_{t-1} itself (coefficients) and L(u_{t-1})
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
               if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
             }
         }
-        L.publish(a.pitch, fld, (t + 1) & 1, pr);
+        L.publish(pitch, fld, (t + 1) & 1, pr);
         if (FIELDS) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -232,10 +235,12 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs 
 // =================================================================================================
 // adjoint
 // =================================================================================================
-template <int R, bool SAT, bool KERR>
-__global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs a) {
-  const int NT = blockDim.x;
-  const int slab_f = (a.Hc + 2) * a.pitch;
+// PITCH / NTC: row pitch and threads per CTA as compile-time constants (0 = from the launch), see wt_resident.cu
+template <int R, bool SAT, bool KERR, int PITCH = 0, int NTC = 0>
+__global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj_nl(ResArgs a) {
+  const int NT = NTC ? NTC : blockDim.x;
+  const int pitch = PITCH ? PITCH : a.pitch;
+  const int slab_f = (a.Hc + 2) * pitch;
   const int RG = a.ring;                        // 2 or 4 (resident_plan)
   const unsigned rg_mask = (unsigned)RG - 1u, rg_shift = RG == 4 ? 2u : 1u;
   const int stage_f4 = 2 * R * NT;
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
     if (pown[p] == tid) {
       if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
     }
-  const int own = (L.lr0 + 1) * a.pitch + 4 + L.j0;
+  const int own = (L.lr0 + 1) * pitch + 4 + L.j0;
   const Scalars s = a.s;
   const float ndtb0 = -s.dt * s.b0, two_iu2 = 2.f * s.inv_uth * s.inv_uth;
 
@@ -326,9 +331,11 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
     stage_seeds((a.T - 1) / TB);
     __syncthreads();
 
-    for (int t = a.T - 1, it = 0; t >= 0; --t, ++it) {
+    // One reverse step; PAR = it & 1 is a compile-time constant of each of the two unrolled copies.
+    auto step = [&](auto par, int t, int it) {
+      constexpr int PAR = decltype(par)::value;
       const int blk = t / TB, tt = t - blk * TB;
-      float* cur = fld + (it & 1) * L.slab;
+      float* cur = fld + PAR * L.slab;
       if ((t == a.T - 1 || tt == TB - 1) && blk > 0) stage_seeds(blk - 1);
       if (a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
       const unsigned gi = it_global + it;
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
             c2[r][k] = (den - 2.f) * ql;                        // new carry (beta-1)*q*lambda, cell.py:42
           }
         }
-        L.publish(a.pitch, fld, it & 1, pv);
+        L.publish(pitch, fld, PAR, pv);
       }
       ++L.npub;
       __syncthreads();
@@ -424,12 +431,22 @@ __global__ void __launch_bounds__(res_nl_max_threads<R>()) k_res_adj_nl(ResArgs 
       L.acquire_ghosts();
       if (L.active) {
         float lapP[R][4];
-        patch_laplacian<R>(a.pitch, cur + own, pv, lapP);
+        patch_laplacian<R>(pitch, cur + own, pv, lapP);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) lam[r][k] += lapP[r][k];
       }
+    };
+    {
+      using P0 = std::integral_constant<int, 0>;
+      using P1 = std::integral_constant<int, 1>;
+      int t = a.T - 1, it = 0;
+      for (; t >= 1; t -= 2, it += 2) {
+        step(P0{}, t, it);
+        step(P1{}, t - 1, it + 1);
+      }
+      if (t == 0) step(P0{}, 0, it);
     }
     it_global += (unsigned)a.T;
     __syncthreads();
@@ -530,8 +547,14 @@ static int nl_launch(K kernel, const wt_plan& plan, size_t smem, const ResArgs& 
 int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
   const int R = plan.rows_per_thread, nl = plan.nonlinear;
   int rc = WT_EINVAL;
+  const char* esp = getenv("WT_RES_NOSPEC");
+  const bool spec = R == 2 && a.pitch == 104 && plan.threads == 480 && !(esp && esp[0] == '1');   // BASELINE config 4
   if (a.fields) {   // output_fields=True: separate instantiation, keeps the field stores out of the common step body
     WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR, true>, plan, plan.smem_fwd, a, st)))
+  } else if (spec) {
+    if (nl == 1) rc = nl_launch(k_res_fwd_nl<2, true, false, false, 104, 480>, plan, plan.smem_fwd, a, st);
+    if (nl == 2) rc = nl_launch(k_res_fwd_nl<2, false, true, false, 104, 480>, plan, plan.smem_fwd, a, st);
+    if (nl == 3) rc = nl_launch(k_res_fwd_nl<2, true, true, false, 104, 480>, plan, plan.smem_fwd, a, st);
   } else {
     WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR>, plan, plan.smem_fwd, a, st)))
   }
@@ -542,7 +565,14 @@ int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
 int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
   const int R = plan.rows_per_thread, nl = plan.nonlinear;
   int rc = WT_EINVAL;
-  WT_NL_ALL((rc = nl_launch(k_res_adj_nl<RR, SAT, KERR>, plan, plan.smem_bwd, a, st)))
+  const char* esp = getenv("WT_RES_NOSPEC");
+  if (R == 2 && a.pitch == 104 && plan.threads == 480 && !(esp && esp[0] == '1')) {   // BASELINE config 4
+    if (nl == 1) rc = nl_launch(k_res_adj_nl<2, true, false, 104, 480>, plan, plan.smem_bwd, a, st);
+    if (nl == 2) rc = nl_launch(k_res_adj_nl<2, false, true, 104, 480>, plan, plan.smem_bwd, a, st);
+    if (nl == 3) rc = nl_launch(k_res_adj_nl<2, true, true, 104, 480>, plan, plan.smem_bwd, a, st);
+  } else {
+    WT_NL_ALL((rc = nl_launch(k_res_adj_nl<RR, SAT, KERR>, plan, plan.smem_bwd, a, st)))
+  }
   if (rc == WT_EINVAL) set_error("nonlinear on-chip kernel R=%d nl=%d not instantiated", R, nl);
   return rc;
 }
