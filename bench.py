@@ -220,7 +220,7 @@ def run_ours(args):
 
     model = build_model(dev)
     runner = BatchShardedWaveRNN(model, average=True) if world > 1 else model
-    opt = torch.optim.Adam(model.parameters(), lr=4e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=4e-4, fused=True)    # torch's single-kernel Adam: same update rule
     x_host = torch.tensor(wo.synthetic_vowels(B, T, first=rank * B)).pin_memory()
     labels_host = ((torch.arange(B) + rank * B) % 3).pin_memory()
     x_dev, labels = x_host.to(dev), labels_host.to(dev)
@@ -271,7 +271,7 @@ def run_ours(args):
     if os.environ.get("WT_BENCH_EAGER", "0") != "1":
         try:
             from wavetorch_b200.graph import GraphedTrainStep
-            opt_g = torch.optim.Adam(model.parameters(), lr=4e-4, capturable=True)
+            opt_g = torch.optim.Adam(model.parameters(), lr=4e-4, capturable=True, fused=True)
             graphed = GraphedTrainStep(
                 runner, opt_g, loss_head,
                 x_dev, labels, warmup=max(args.warmup, 3))

@@ -243,8 +243,12 @@ class WaveGeometryFreeForm(WaveGeometry):
         Written as a masked select instead of boolean-mask assignment: same result, but no host synchronisation (the
         mask assignment has to count its True entries on the host) and therefore capturable in a CUDA graph."""
         with torch.no_grad():
-            keep = (self.design_region != 0) & ~(self.b > 0)
-            self.rho.copy_(torch.where(keep, self.rho, torch.zeros_like(self.rho)))
+            key = (self.design_region.data_ptr(), self.design_region._version, self._b.data_ptr(), self._b._version)
+            cached = getattr(self, "_drop_mask", None)
+            if cached is None or cached[0] != key:      # both inputs are static buffers: build the mask once
+                cached = (key, ~((self.design_region != 0) & ~(self.b > 0)))
+                self._drop_mask = cached
+            self.rho.masked_fill_(cached[1], 0.0)        # one kernel per training iteration
 
     def _apply_blur(self, rho):
         """blur_N passes of the zero-padded disk stencil (geom.py:207-215).
