@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 // i.e. exactly the forward update (wt_update) run backwards in time, with the probe seeds playing the role of the
 // sources.  So this kernel is the forward kernel plus the tape: sum_t L(u_{t-1})*P_t accumulates per cell and
 // dLoss/dc = gscale * sum / a3 = (2/c) * sum  (cell.py:36).  dLoss/dx[b,t] = sum over source pixels of P_t/a3.
-template <int R, int PITCH = 0, int NTC = 0>
+// GRADX = 0: dLoss/dx is not wanted, its code is compiled out (shape-specialised instances only); 1: decided at run time.
+template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   const int NT = NTC ? NTC : blockDim.x;
   const int pitch = PITCH ? PITCH : a.pitch;
@@ -343,13 +344,13 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       if (tt == TB - 1 && t != a.T - 1) {
         const int blk = t / TB;
         if (blk > 0) stage_seeds(blk - 1);
-        if (a.grad_x) flush_gx(blk + 1);
+        if (GRADX && a.grad_x) flush_gx(blk + 1);
       }
       const unsigned gi = it_global + it;
       const unsigned slot = gi & (RING - 1), parity = (gi / RING) & 1u;
       L.acquire_ghosts();
       if (L.active) {
-        if (a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
+        if (GRADX && a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
           // a loop over the (few) source cells of this thread with one division each: 4R unrolled divisions would
           // triple the size of the step body for code that one thread per sample executes
           float s = 0.f;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     if (t == 0) step(P0{}, v, w, 0, it);
     it_global += (unsigned)a.T;
     __syncthreads();
-    if (a.grad_x) flush_gx(0);
+    if (GRADX && a.grad_x) flush_gx(0);
     __syncthreads();
   }
   // per-cluster partial of sum_{b,t} L(u_{t-1})*P_t ; reduced and scaled by 2/c in k_finish_grad_p
@@ -712,7 +713,8 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
   }
   const char* esp = getenv("WT_RES_NOSPEC");
   if (plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(esp && esp[0] == '1')) {   // BASELINE config 3
-    WT_TRY(launch_cluster(k_res_adj<5, 104, 384>, plan, plan.smem_bwd, a, st));
+    if (a.grad_x) WT_TRY(launch_cluster(k_res_adj<5, 104, 384, 1>, plan, plan.smem_bwd, a, st));
+    else WT_TRY(launch_cluster(k_res_adj<5, 104, 384, 0>, plan, plan.smem_bwd, a, st));
   } else {
     WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st)));
   }
