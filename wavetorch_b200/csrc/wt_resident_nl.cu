@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
 // adjoint
 // =================================================================================================
 // PITCH / NTC: row pitch and threads per CTA as compile-time constants (0 = from the launch), see wt_resident.cu
-template <int R, bool SAT, bool KERR, int PITCH = 0, int NTC = 0>
+// GRADX = 0: dLoss/dx code compiled out (shape-specialised instances only); 1: decided at run time
+template <int R, bool SAT, bool KERR, int PITCH = 0, int NTC = 0, int GRADX = 1>
 __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj_nl(ResArgs a) {
   const int NT = NTC ? NTC : blockDim.x;
   const int pitch = PITCH ? PITCH : a.pitch;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       const int blk = t / TB, tt = t - blk * TB;
       float* cur = fld + PAR * L.slab;
       if ((t == a.T - 1 || tt == TB - 1) && blk > 0) stage_seeds(blk - 1);
-      if (a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
+      if (GRADX && a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
       const unsigned gi = it_global + it;
       const unsigned slot = gi & rg_mask, parity = (gi >> rg_shift) & 1u;
       const unsigned slot2 = (gi + 1) & rg_mask, parity2 = ((gi + 1) >> rg_shift) & 1u;   // stage of step t-1: its u is my u_{t-2}
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
               }
           }
         }
-        if (a.grad_x && m1) {
+        if (GRADX && a.grad_x && m1) {
           float sv = 0.f;
 #pragma unroll
           for (int r = 0; r < R; ++r)
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
     }
     it_global += (unsigned)a.T;
     __syncthreads();
-    if (a.grad_x) flush_gx(0);
+    if (GRADX && a.grad_x) flush_gx(0);
     __syncthreads();
   }
   const size_t plane = (size_t)a.Nx * a.Ny;
@@ -567,9 +568,15 @@ int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
   int rc = WT_EINVAL;
   const char* esp = getenv("WT_RES_NOSPEC");
   if (R == 2 && a.pitch == 104 && plan.threads == 480 && !(esp && esp[0] == '1')) {   // BASELINE config 4
-    if (nl == 1) rc = nl_launch(k_res_adj_nl<2, true, false, 104, 480>, plan, plan.smem_bwd, a, st);
-    if (nl == 2) rc = nl_launch(k_res_adj_nl<2, false, true, 104, 480>, plan, plan.smem_bwd, a, st);
-    if (nl == 3) rc = nl_launch(k_res_adj_nl<2, true, true, 104, 480>, plan, plan.smem_bwd, a, st);
+    if (a.grad_x) {
+      if (nl == 1) rc = nl_launch(k_res_adj_nl<2, true, false, 104, 480, 1>, plan, plan.smem_bwd, a, st);
+      if (nl == 2) rc = nl_launch(k_res_adj_nl<2, false, true, 104, 480, 1>, plan, plan.smem_bwd, a, st);
+      if (nl == 3) rc = nl_launch(k_res_adj_nl<2, true, true, 104, 480, 1>, plan, plan.smem_bwd, a, st);
+    } else {
+      if (nl == 1) rc = nl_launch(k_res_adj_nl<2, true, false, 104, 480, 0>, plan, plan.smem_bwd, a, st);
+      if (nl == 2) rc = nl_launch(k_res_adj_nl<2, false, true, 104, 480, 0>, plan, plan.smem_bwd, a, st);
+      if (nl == 3) rc = nl_launch(k_res_adj_nl<2, true, true, 104, 480, 0>, plan, plan.smem_bwd, a, st);
+    }
   } else {
     WT_NL_ALL((rc = nl_launch(k_res_adj_nl<RR, SAT, KERR>, plan, plan.smem_bwd, a, st)))
   }

@@ -283,7 +283,8 @@ struct TileAdjArgs {
   int out_lambda;             // last launch of a chained call: V1 = dLoss/du1_in = P_{-1}/a3, V2 = dLoss/du2_in = (1-a1)*P_0/a3
 };
 
-template <int R>
+// GRADX: dLoss/dx is wanted (its gather is compiled out otherwise: the step body is fetched 2K times per tile)
+template <int R, bool GRADX>
 __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs aa) {
   const TileArgs& a = aa.g;
   extern __shared__ float4 smem4[];
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
   tile_load_coef<R>(a.a1, a.a3, active, gi0, gj0, a.Nx, a.Ny, k1, k3);
   // sources among my OWNED cells (dLoss/dx gathers each source pixel exactly once)
   unsigned m1 = 0, m2 = 0, m3 = 0;
-  if (aa.grad_x && col_in)
+  if (GRADX && col_in)
     for (int s = 0; s < a.n_src; ++s) {
       const int si = a.src_ij[2 * s] - gi0, sj = a.src_ij[2 * s + 1] - gj0;
       if (si >= 0 && si < R && sj >= 0 && sj < 4 && lr0 + si >= a.K && lr0 + si < a.K + a.TH) {
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
       const int t = a.t0 - J;
       const float* cur = fld + (J & 1) * slab;
       float* nxt = fld + ((J + 1) & 1) * slab;
-      if (m1) {   // dLoss/dx[b,t] = sum over source pixels of lambda_t = P_t / a3 (loop over my few source cells)
+      if (GRADX && m1) {   // dLoss/dx[b,t] = sum over source pixels of lambda_t = P_t / a3 (loop over my few source cells)
         float sx = 0.f;
         for (unsigned mm = m1; mm; mm &= mm - 1u) {
           const int bit = __ffs(mm) - 1;
@@ -641,6 +642,13 @@ int tile_forward(const wt_problem* p, const float* a1, const float* a3, const fl
 int tile_launches_fwd(const wt_problem* p) { const int K = tile_geom(p).K; return (p->T + K - 1) / K + 1; }
 int tile_launches_bwd(const wt_problem* p) { return (p->T + TILE_ADJ_K - 1) / TILE_ADJ_K + 2; }
 
+template <int R, bool GX>
+static int launch_tile_adj(dim3 grid, dim3 block, size_t smem, cudaStream_t st, const TileAdjArgs& aa) {
+  WT_CUDA(cudaFuncSetAttribute(k_tile_adj<R, GX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tile_adj<R, GX><<<grid, block, smem, st>>>(aa);
+  return WT_OK;
+}
+
 size_t tile_extra_ws_bwd_bytes(const wt_problem* p) {
   // one more [B,plane] field so that (adj1,adj2)/(w1,w2) always have a ping-pong partner pair
   return tile_eligible(p) ? (size_t)p->B * p->Nx * p->Ny * sizeof(float) + 256 : 0;
@@ -681,20 +689,14 @@ int tile_backward(const wt_problem* p, const float* a1, const float* a3, const f
     aa.premul_first = aa.in_lambda = (t_hi == p->T - 1) ? 1 : 0;
     aa.out_lambda = (chained && t_hi - g.K < 0) ? 1 : 0;
     dim3 grid(ntiles, nby), block(g.threads);
+    const bool gx = grad_x != nullptr;
+    int rc;
     switch (g.R) {
-      case 2:
-        WT_CUDA(cudaFuncSetAttribute(k_tile_adj<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tile_adj<2><<<grid, block, smem, st>>>(aa);
-        break;
-      case 3:
-        WT_CUDA(cudaFuncSetAttribute(k_tile_adj<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tile_adj<3><<<grid, block, smem, st>>>(aa);
-        break;
-      default:
-        WT_CUDA(cudaFuncSetAttribute(k_tile_adj<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tile_adj<4><<<grid, block, smem, st>>>(aa);
-        break;
+      case 2: rc = gx ? launch_tile_adj<2, true>(grid, block, smem, st, aa) : launch_tile_adj<2, false>(grid, block, smem, st, aa); break;
+      case 3: rc = gx ? launch_tile_adj<3, true>(grid, block, smem, st, aa) : launch_tile_adj<3, false>(grid, block, smem, st, aa); break;
+      default: rc = gx ? launch_tile_adj<4, true>(grid, block, smem, st, aa) : launch_tile_adj<4, false>(grid, block, smem, st, aa); break;
     }
+    WT_TRY(rc);
     float* s1 = A1; float* s2 = A2; A1 = B1; A2 = B2; B1 = s1; B2 = s2;
   }
   WT_CUDA(cudaGetLastError());
