@@ -284,26 +284,27 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     };
     // P += a3 * seed_t at the probe cells of my patch.  The common case (at most one probe per thread) needs one shared
     // load and a compile-time unrolled select; further probes of the same thread go through the general loop.
+    // (the seed of a cell is added with four FMAs on its row, three of them with a zero addend: selecting the row costs
+    //  R compares, selecting the single register would cost a 4R-way jump table in every copy of the step body)
+    auto add_seed_cell = [&](float (&P)[R][4], int pc, float sv) {
+      const int prow = pc >> 2, pcol = pc & 3;
+      const float s0 = pcol == 0 ? sv : 0.f, s1 = pcol == 1 ? sv : 0.f, s2 = pcol == 2 ? sv : 0.f, s3 = pcol == 3 ? sv : 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (prow == r) {
+          P[r][0] = fmaf(k3[r][0], s0, P[r][0]);
+          P[r][1] = fmaf(k3[r][1], s1, P[r][1]);
+          P[r][2] = fmaf(k3[r][2], s2, P[r][2]);
+          P[r][3] = fmaf(k3[r][3], s3, P[r][3]);
+        }
+    };
     auto add_seeds = [&](float (&P)[R][4], int t) {
       if (pc0 >= 0) {
         const float* srow = ss + (t & (2 * TB - 1)) * a.n_prb;
-        const float sv = srow[pi0];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (pc0 == r * 4 + k) P[r][k] = fmaf(k3[r][k], sv, P[r][k]);
+        add_seed_cell(P, pc0, srow[pi0]);
         if (more_probes) {
           for (int p = pi0 + 1; p < a.n_prb; ++p)
-            if (pown[p] == tid) {
-              const float sw = srow[p];
-              const int pc = pcell[p];
-#pragma unroll
-              for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (pc == r * 4 + k) P[r][k] = fmaf(k3[r][k], sw, P[r][k]);
-            }
+            if (pown[p] == tid) add_seed_cell(P, pcell[p], srow[p]);
         }
       }
     };
@@ -339,13 +340,6 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     auto step = [&](auto par, float (&cu)[R][4], float (&pr)[R][4], int t, int it) {
       constexpr int PAR = decltype(par)::value;
       const float* cur = PAR ? rd1 : rd0;
-      const int tt = t & (TB - 1);
-      // staging bookkeeping, once per block of TB steps: seeds two blocks ahead, dLoss/dx of the block just finished
-      if (tt == TB - 1 && t != a.T - 1) {
-        const int blk = t / TB;
-        if (blk > 0) stage_seeds(blk - 1);
-        if (GRADX && a.grad_x) flush_gx(blk + 1);
-      }
       const unsigned gi = it_global + it;
       const unsigned slot = gi & (RING - 1), parity = (gi / RING) & 1u;
       L.acquire_ghosts();
@@ -400,8 +394,17 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     using P1 = std::integral_constant<int, 1>;
     int t = a.T - 1, it = 0;
     for (; t >= 1; t -= 2, it += 2) {
+      // Staging bookkeeping, once per block of TB steps and outside the step bodies (their code size is what the
+      // instruction cache sees 2T times per sample).  When a block starts at the second step of the pair its seeds are
+      // staged one step early: the half they go to held the seeds of the block before the previous one, all consumed.
+      const int tb = ((t & (TB - 1)) == TB - 1) ? t : ((((t - 1) & (TB - 1)) == TB - 1) ? t - 1 : -1);
+      if (tb >= 0 && tb != a.T - 1 && tb >= TB) stage_seeds(tb / TB - 1);
       step(P0{}, v, w, t, it);
       step(P1{}, w, v, t - 1, it + 1);
+      if (GRADX && a.grad_x) {   // dLoss/dx of a block goes out right after its last (lowest) step
+        if ((t & (TB - 1)) == 0 && t >= TB) flush_gx(t / TB);
+        if (((t - 1) & (TB - 1)) == 0 && t - 1 >= TB) flush_gx((t - 1) / TB);
+      }
     }
     if (t == 0) step(P0{}, v, w, 0, it);
     it_global += (unsigned)a.T;
