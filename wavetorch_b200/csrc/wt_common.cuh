@@ -96,4 +96,50 @@ __device__ __forceinline__ CellCoef wt_coef(const Scalars& s, float b, float c) 
   return k;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rare-cell updates of a thread's R x 4 register patch (sources, probe seeds).  They are executed by one or two threads per
+// sample but sit inside the time-step body of every thread: selecting the ROW with R compares and touching its four
+// registers (three of them with a zero addend) keeps that code to a few instructions; selecting the single register
+// would take a 4R-way branch tree in every unrolled copy of the step and puts ~100 instructions on the critical
+// path of the owning warp, which every other warp then waits for at the step's barrier.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void patch_add_cell(float (&P)[R][4], int cell, float v) {   // P[cell] += v
+  const int prow = cell >> 2, pcol = cell & 3;
+  const float s0 = pcol == 0 ? v : 0.f, s1 = pcol == 1 ? v : 0.f, s2 = pcol == 2 ? v : 0.f, s3 = pcol == 3 ? v : 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (prow == r) { P[r][0] += s0; P[r][1] += s1; P[r][2] += s2; P[r][3] += s3; }
+}
+template <int R>
+__device__ __forceinline__ void patch_fma_cell(float (&P)[R][4], const float (&K)[R][4], int cell, float v) {   // P[cell] += K[cell]*v
+  const int prow = cell >> 2, pcol = cell & 3;
+  const float s0 = pcol == 0 ? v : 0.f, s1 = pcol == 1 ? v : 0.f, s2 = pcol == 2 ? v : 0.f, s3 = pcol == 3 ? v : 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (prow == r) {
+      P[r][0] = fmaf(K[r][0], s0, P[r][0]);
+      P[r][1] = fmaf(K[r][1], s1, P[r][1]);
+      P[r][2] = fmaf(K[r][2], s2, P[r][2]);
+      P[r][3] = fmaf(K[r][3], s3, P[r][3]);
+    }
+}
+// P += x at the cells listed in m1, once more at those in m2 and m3 (bit r*4+k = cell (r,k)); source.py:19-22
+template <int R>
+__device__ __forceinline__ void patch_inject(float (&P)[R][4], unsigned m1, unsigned m2, unsigned m3, float x) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const unsigned a = (m1 >> (4 * r)) & 0xFu;
+    if (a) {
+      const unsigned b = (m2 >> (4 * r)) & 0xFu, c = (m3 >> (4 * r)) & 0xFu;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        P[r][k] += (a >> k & 1u) ? x : 0.f;
+        P[r][k] += (b >> k & 1u) ? x : 0.f;
+        P[r][k] += (c >> k & 1u) ? x : 0.f;
+      }
+    }
+  }
+}
+
 }  // namespace wt

@@ -113,14 +113,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         if (m1) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t]
-          const float xv = xs[t & (2 * TB - 1)];
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (m1 >> (r * 4 + k) & 1u) pr[r][k] += xv;
-              if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
-            }
+          patch_inject<R>(pr, m1, m2, 0u, xs[t & (2 * TB - 1)]);
         }
         L.publish(pitch, fld, PAR ^ 1, pr);
         if (TAPE) {
@@ -284,27 +277,13 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     };
     // P += a3 * seed_t at the probe cells of my patch.  The common case (at most one probe per thread) needs one shared
     // load and a compile-time unrolled select; further probes of the same thread go through the general loop.
-    // (the seed of a cell is added with four FMAs on its row, three of them with a zero addend: selecting the row costs
-    //  R compares, selecting the single register would cost a 4R-way jump table in every copy of the step body)
-    auto add_seed_cell = [&](float (&P)[R][4], int pc, float sv) {
-      const int prow = pc >> 2, pcol = pc & 3;
-      const float s0 = pcol == 0 ? sv : 0.f, s1 = pcol == 1 ? sv : 0.f, s2 = pcol == 2 ? sv : 0.f, s3 = pcol == 3 ? sv : 0.f;
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (prow == r) {
-          P[r][0] = fmaf(k3[r][0], s0, P[r][0]);
-          P[r][1] = fmaf(k3[r][1], s1, P[r][1]);
-          P[r][2] = fmaf(k3[r][2], s2, P[r][2]);
-          P[r][3] = fmaf(k3[r][3], s3, P[r][3]);
-        }
-    };
     auto add_seeds = [&](float (&P)[R][4], int t) {
       if (pc0 >= 0) {
         const float* srow = ss + (t & (2 * TB - 1)) * a.n_prb;
-        add_seed_cell(P, pc0, srow[pi0]);
+        patch_fma_cell<R>(P, k3, pc0, srow[pi0]);
         if (more_probes) {
           for (int p = pi0 + 1; p < a.n_prb; ++p)
-            if (pown[p] == tid) add_seed_cell(P, pcell[p], srow[p]);
+            if (pown[p] == tid) patch_fma_cell<R>(P, k3, pcell[p], srow[p]);
         }
       }
     };

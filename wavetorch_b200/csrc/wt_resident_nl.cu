@@ -162,16 +162,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
             }
             pr[r][k] = wt_update(q + q, q * kc2, u, pr[r][k], lap[r][k]);
           }
-        if (m1) {
-          const float xv = xs[(blk & 1) * TB + tt];
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (m1 >> (r * 4 + k) & 1u) pr[r][k] += xv;
-              if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
-            }
-        }
+        if (m1) patch_inject<R>(pr, m1, m2, 0u, xs[(blk & 1) * TB + tt]);
         L.publish(pitch, fld, (t + 1) & 1, pr);
         if (FIELDS) {
 #pragma unroll
@@ -346,23 +337,10 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       if (L.active) {
         if (pc0 >= 0) {   // lambda_t += dLoss/du_t through the probes (first probe of my patch: fast path)
           const float* srow = ss + (blk & 1) * TB * a.n_prb + tt * a.n_prb;
-          const float sv = srow[pi0];
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (pc0 == r * 4 + k) lam[r][k] += sv;
+          patch_add_cell<R>(lam, pc0, srow[pi0]);
           if (more_probes) {
             for (int p = pi0 + 1; p < a.n_prb; ++p)
-              if (pown[p] == tid) {
-                const float sw = srow[p];
-                const int pc = pcell[p];
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (pc == r * 4 + k) lam[r][k] += sw;
-              }
+              if (pown[p] == tid) patch_add_cell<R>(lam, pcell[p], srow[p]);
           }
         }
         if (GRADX && a.grad_x && m1) {

@@ -208,17 +208,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
-        if (m1) {
-          const float xv = xsb[J];
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (m1 >> (r * 4 + k) & 1u) pr[r][k] += xv;
-              if (m2 >> (r * 4 + k) & 1u) pr[r][k] += xv;
-              if (m3 >> (r * 4 + k) & 1u) pr[r][k] += xv;
-            }
-        }
+        if (m1) patch_inject<R>(pr, m1, m2, m3, xsb[J]);
 #pragma unroll
         for (int r = 0; r < R; ++r)
           *reinterpret_cast<float4*>(nxt + own + r * a.pitch) = make_float4(pr[r][0], pr[r][1], pr[r][2], pr[r][3]);
@@ -459,12 +449,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
               const size_t o = ((size_t)b * a.T + (t - 1)) * a.n_prb + pid[p];
               float sv = aa.grad_probe[o];
               if (a.prb_sq[pid[p]]) sv *= 2.f * a.probe_raw[o];
-              const int pc = pcel[p];
-#pragma unroll
-              for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (pc == r * 4 + k) pr[r][k] = fmaf(k3[r][k], sv, pr[r][k]);
+              patch_fma_cell<R>(pr, k3, pcel[p], sv);
             }
         }
 #pragma unroll
