@@ -73,7 +73,7 @@ if os.path.exists(os.path.join(G, "configs.md")):
     if os.path.exists(p2):
         d2 = json.load(open(p2))
         t.append(f"| 5 window, 2 GPUs (row slabs) | + domain decomposition, halo 16 | {d2['fwd']['ms_per_step']:.2f} | {d2['fwd']['value']:.1f} | {d2['ms_per_step']:.2f} | {d2['value']:.1f} | |")
-    t.append("| 5 window 4096x4096 B=8 T=40, no checkpoints (tools/time_large.py) | streaming, K=4 tiles | 7.52 | 713.6 | 20.3 | 264.8 | |")
+    t.append("| 5 window 4096x4096 B=8 T=40, no checkpoints (tools/time_large.py) | streaming, K=4 tiles | 7.60 | 706 | 20.2 | 265.5 | |")
     t.append("")
     t.append("Roofline reference (SURVEY 8d, measured HBM copy peak 6553.9 GB/s): 546 Gcell/s forward (12 B/update), 205 Gcell/s fwd+bwd (32 B/update); the 60 % target is 328 / 123.")
     dref = json.load(open(os.path.join(P, "r1_bench_reference_n1.json")))
@@ -83,7 +83,7 @@ if os.path.exists(os.path.join(G, "configs.md")):
         if os.path.exists(pn):
             line += f", {json.load(open(pn))['value']:.1f} on {n} GPUs"
     t.append(line + f"; CPU port of the reference on the box's {dref['cpu_baseline']['cores']} cores: {dref['value']:.3f} (`--impl reference`), {d['cpu_baseline']['value']:.3f} (cpu_baseline of the same run).")
-    t.append("History of config 3 fwd+bwd (kernels only): 341 (first complete version) -> 387 (P-form adjoint, seed fast path) -> 404 (compile-time pitch/threads) -> 417 (dLoss/dx gather out of the unrolled step body) -> 423 (fields output in its own instantiation) -> 435 (dLoss/dx code compiled out when x.grad is not requested).")
+    t.append("History of config 3 fwd+bwd (kernels only): 341 (first complete version) -> 387 (P-form adjoint, seed fast path) -> 404 (compile-time pitch/threads) -> 417 (dLoss/dx gather out of the unrolled step body) -> 423 (fields output in its own instantiation) -> 435 (dLoss/dx code compiled out when x.grad is not requested) -> 480 (adjoint: per-block staging out of the step bodies, seeds added row-wise) -> 497 (sources added row-wise).")
     t.append("History of config 4 fwd+bwd: 104 / 99 / 100 (first version) -> 187 / 169 (one or two MUFU reciprocals per cell) -> 236 / 205 / 230 (ring arithmetic, compile-time parity and shape, dLoss/dx compiled out).")
     if stress:
         t.append("Stress: " + stress[0].replace("stress: ", ""))
