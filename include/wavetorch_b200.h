@@ -72,7 +72,9 @@ typedef struct wt_problem {
   /* tuning overrides, 0 = automatic */
   int32_t cluster;  /* CTAs per sample (resident path): 1,2,4,8,16 */
   int32_t rows_per_thread;
-  int32_t reserved[6];
+  int32_t field_every; /* fields_out keeps every field_every-th field only (0 or 1 = all): snapshot k is the field after
+                          step (k+1)*field_every - 1, k < T / field_every.  Forward/inference only. */
+  int32_t reserved[5];
 } wt_problem;
 
 /* What wt_forward/wt_backward will do for a problem, and how much caller-provided scratch they need. */
@@ -110,7 +112,8 @@ int wt_query_plan(const wt_problem* p, wt_plan* plan);
  *   u1, u2      [B,Nx,Ny] in: fields at t-1 and t-2 (ignored with WT_F_ZERO_INIT); out: the two latest fields
  *   probe_out   [B,T,n_prb] probe readout (squared where prb_square), the reference's model(x) output
  *   probe_raw   [B,T,n_prb] field at the probes (needed by wt_backward); may be NULL
- *   fields_out  [B,T,Nx,Ny] every field (output_fields=True, rnn.py:65-67); may be NULL.  Together with `history` it
+ *   fields_out  [B,T,Nx,Ny] every field (output_fields=True, rnn.py:65-67), or [B,T/field_every,Nx,Ny] time-decimated
+ *               snapshots when p->field_every > 1 (not together with `history`); may be NULL.  Together with `history` it
  *               needs WT_F_FORCE_STREAM (dLoss/dfields is implemented by the streaming adjoint); WT_EUNSUPPORTED otherwise
  *   history     adjoint tape of plan.history_bytes, or NULL for inference
  *   workspace   plan.workspace_fwd_bytes

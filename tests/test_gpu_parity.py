@@ -706,3 +706,25 @@ def test_train_loop_matches_reference_history(tmp_path):
     h3, _ = wt.train(model2, torch.optim.Adam(model2.parameters(), lr=0.02), torch.nn.CrossEntropyLoss(label_smoothing=0.0, reduction="sum"),
                      train_dl, None, 0, bs, history_model_state=[])
     assert abs(h3["loss_train"].iloc[0] / bs - g["loss_train"][0]) < 2e-4
+
+
+@pytest.mark.parametrize("b0,uth,cnl", [(0.0, 0.0, 0.0), (0.3, 0.7, -0.1)])
+@pytest.mark.parametrize("path,flags", PATHS)
+def test_time_decimated_field_snapshots(path, flags, b0, uth, cnl):
+    """output_fields with field_every=k returns exactly every k-th field of the full [B,T,Nx,Ny] output, on
+    both paths, linear and nonlinear; with a gradient requested it refuses."""
+    Nx, Ny, N, B, T, k = 44, 40, 5, 3, 50, 7
+    geom = wt.WaveGeometryFreeForm((Nx, Ny), 1.0, 1.0, 0.6, abs_N=N, abs_sig=3.0, abs_p=3.0, rho='half')
+    m = wt.WaveRNN(wt.WaveCell(0.6, geom, satdamp_b0=b0, satdamp_uth=uth, c_nl=cnl), [wt.WaveSource(8, 20)],
+                   [wt.WaveIntensityProbe(35, 14)]).to(DEV)
+    m.plan_flags = flags
+    x = torch.tensor((0.3 * np.random.RandomState(5).randn(B, T)).astype(np.float32), device=DEV)
+    with torch.no_grad():
+        full = m(x, output_fields=True)
+        dec = m(x, output_fields=True, field_every=k)
+        one = m(x, output_fields=True, field_every=1)
+    assert full.shape == (B, T, Nx, Ny) and dec.shape == (B, T // k, Nx, Ny)
+    assert torch.equal(dec, full[:, k - 1::k][:, :T // k])
+    assert torch.equal(one, full)
+    with pytest.raises(NotImplementedError):
+        m(x, output_fields=True, field_every=k)

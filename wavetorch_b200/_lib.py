@@ -28,7 +28,8 @@ class WtProblem(ctypes.Structure):
                 ("n_src", ctypes.c_int32), ("n_prb", ctypes.c_int32), ("flags", ctypes.c_uint32),
                 ("device", ctypes.c_int32), ("dt", ctypes.c_double), ("h", ctypes.c_double),
                 ("b0", ctypes.c_double), ("uth", ctypes.c_double), ("c_nl", ctypes.c_double),
-                ("cluster", ctypes.c_int32), ("rows_per_thread", ctypes.c_int32), ("reserved", ctypes.c_int32 * 6)]
+                ("cluster", ctypes.c_int32), ("rows_per_thread", ctypes.c_int32), ("field_every", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 5)]
 
 
 class WtPlan(ctypes.Structure):

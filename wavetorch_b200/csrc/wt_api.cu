@@ -99,6 +99,8 @@ int wt_forward(const wt_problem* p, const float* c, const float* b, const float*
   wt_plan plan;
   WT_TRY(make_plan(p, true, false, &plan));
   WT_REQUIRE(c && b && x && u1 && u2, "wt_forward: c, b, x, u1, u2 must not be NULL");
+  WT_REQUIRE(p->field_every >= 0 && (p->field_every <= 1 || !history),
+             "wt_forward: field_every=%d (time-decimated fields_out) is a forward-only mode", p->field_every);
   WT_REQUIRE(!plan.nonlinear || rho, "wt_forward: rho is required when b0 > 0 or c_nl != 0");
   WT_REQUIRE(p->n_src == 0 || src_ij, "wt_forward: src_ij is NULL");
   WT_REQUIRE(p->n_prb == 0 || (prb_ij && prb_square), "wt_forward: prb_ij / prb_square is NULL");

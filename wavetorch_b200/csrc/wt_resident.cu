@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
     __syncthreads();
 
     float4* tape = TAPE ? a.tape + (((size_t)b * a.T) * a.C + L.rank) * R * NT + tid : nullptr;
-    float* fout = FIELDS ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
+    float* fout = FIELDS ? a.fields + ((size_t)b * (a.T / a.field_every)) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
 
     auto flush = [&](int blk) {   // probe samples of time block blk -> HBM
       const int t0 = blk * TB, n = min(TB, a.T - t0);
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
           for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
           tape += tape_step;
         }
-        if (FIELDS) {
+        if (FIELDS && (t + 1) % a.field_every == 0) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (L.gi0 + r < a.Nx) {
@@ -588,6 +588,7 @@ static void fill_args(const wt_problem* p, const wt_plan& plan, ResArgs* a) {
   a->C = plan.cluster; a->Hc = plan.rows_per_cta; a->P4 = (p->Ny + 3) / 4; a->pitch = 4 * a->P4 + 4;
   a->runs = plan.rows_per_cta / plan.rows_per_thread; a->nact = a->runs * a->P4;
   a->n_src = p->n_src; a->n_prb = p->n_prb; a->n_clusters = plan.n_clusters; a->flags = p->flags;
+  a->field_every = p->field_every > 1 ? p->field_every : 1;
 }
 
 template <typename K>

@@ -18,6 +18,7 @@ struct ResArgs {
   int n_src, n_prb, n_clusters;
   unsigned flags;
   int vec_fields;            // fields_out may be written with float4
+  int field_every;           // >= 1: every field_every-th field goes to fields_out
   const float* a1;
   const float* a3;
   const float* x;

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
     __syncthreads();
 
     float4* tape = a.tape ? a.tape + (((size_t)b * a.T) * a.C + L.rank) * 2 * R * NT + tid : nullptr;
-    float* fout = FIELDS ? a.fields + ((size_t)b * a.T) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
+    float* fout = FIELDS ? a.fields + ((size_t)b * (a.T / a.field_every)) * plane + (size_t)L.gi0 * a.Ny + L.j0 : nullptr;
 
     auto flush = [&](int blk) {
       const int t0 = blk * TB, n = min(TB, a.T - t0);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
           }
         if (m1) patch_inject<R>(pr, m1, m2, 0u, xs[(blk & 1) * TB + tt]);
         L.publish(pitch, fld, (t + 1) & 1, pr);
-        if (FIELDS) {
+        if (FIELDS && (t + 1) % a.field_every == 0) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             if (L.gi0 + r < a.Nx) {

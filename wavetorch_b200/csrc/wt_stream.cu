@@ -533,8 +533,9 @@ int stream_forward(const wt_problem* p, const float* c, const float* b, const fl
     a.tape_lap = (tape && !general) ? tape + (size_t)t * field : nullptr;
     a.tape_u1 = (tape && general) ? tape + (size_t)(t + 1) * field : nullptr;
     a.tape_u2 = (tape && general && t == 0) ? tape : nullptr;
-    a.fields = fields_out ? fields_out + (size_t)t * plane : nullptr;
-    a.fields_bstride = (size_t)p->T * plane;
+    const int fe = p->field_every > 1 ? p->field_every : 1;      // time-decimated snapshots: step t -> slot t / fe
+    a.fields = (fields_out && (t + 1) % fe == 0) ? fields_out + (size_t)(t / fe) * plane : nullptr;
+    a.fields_bstride = (size_t)(p->T / fe) * plane;
     a.s = s;
     dim3 grid = stream_grid(p->Nx, p->Ny, vec, nbz), block(32, 4);
 #define WT_LAUNCH_FWD(V)                                                          \

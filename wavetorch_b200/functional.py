@@ -44,6 +44,7 @@ class LoopSpec:
     uth: float = 0.0
     c_nl: float = 0.0
     output_fields: bool = False
+    field_every: int = 1        # output_fields only: keep every field_every-th field (time-decimated snapshots, no gradient)
     flags: int = 0
     cluster: int = 0
     rows_per_thread: int = 0
@@ -225,12 +226,18 @@ class _WaveLoop(torch.autograd.Function):
         prob = _lib.make_problem(Nx, Ny, B, T, n_src, n_prb, spec.dt, spec.h, spec.b0, spec.uth, spec.c_nl, flags,
                                  dev.index if dev.index is not None else torch.cuda.current_device(), spec.cluster,
                                  spec.rows_per_thread)
+        fe = int(spec.field_every) if spec.output_fields else 1
+        if fe > 1:
+            if want_grad:
+                raise NotImplementedError("wavetorch_b200: time-decimated field output (field_every > 1) is a forward-only "
+                                          "mode; call it under torch.no_grad()")
+            prob.field_every = fe
         plan = _lib.query_plan(prob)
         u1 = torch.empty((B, Nx, Ny), device=dev, dtype=torch.float32)
         u2 = torch.empty((B, Nx, Ny), device=dev, dtype=torch.float32)
         probe_out = torch.empty((B, T, n_prb), device=dev, dtype=torch.float32)
         probe_raw = torch.empty((B, T, n_prb), device=dev, dtype=torch.float32) if want_grad else None
-        fields = torch.empty((B, T, Nx, Ny), device=dev, dtype=torch.float32) if spec.output_fields else None
+        fields = torch.empty((B, T // max(fe, 1), Nx, Ny), device=dev, dtype=torch.float32) if spec.output_fields else None
         ws = torch.empty(max(int(plan.workspace_fwd_bytes), 16), device=dev, dtype=torch.uint8)
         hist = torch.empty(max(int(plan.history_bytes), 16), device=dev, dtype=torch.uint8) if want_grad else None
         with torch.cuda.device(dev):

@@ -60,18 +60,23 @@ class WaveRNN(torch.nn.Module):
         return tables
 
     # ------------------------------------------------------------------
-    def forward(self, x, output_fields=False):
+    def forward(self, x, output_fields=False, field_every=1):
         """Propagate for the length of the inputs.
 
         x : [B, T] input sequences (batch first).  Returns the probe time series [B, T, n_probes]
         (squared for WaveIntensityProbe), or all fields [B, T, Nx, Ny] when there are no probes or
         `output_fields` is set (rnn.py:21-72).
+
+        field_every (extension): with output_fields, keep only every field_every-th field --
+        [B, T // field_every, Nx, Ny], snapshot k being the field after step (k+1)*field_every - 1, i.e.
+        `model(x, output_fields=True)[:, field_every-1::field_every]` without materialising the full history (what the
+        reference's plotting code slices afterwards, plot.py:203-243).  Forward-only: use it under torch.no_grad().
         """
         geom = self.cell.geom
         # evaluated once per forward, like rnn.py:46-47
-        return self._run(x, geom.c, geom.b, geom.rho, output_fields)
+        return self._run(x, geom.c, geom.b, geom.rho, output_fields, field_every)
 
-    def _run(self, x, c, b, rho, output_fields=False):
+    def _run(self, x, c, b, rho, output_fields=False, field_every=1):
         if x.dim() != 2:
             raise ValueError("WaveRNN expects x of shape [batch, time], got %s" % (tuple(x.shape),))
         geom = self.cell.geom
@@ -87,7 +92,8 @@ class WaveRNN(torch.nn.Module):
             geom._h_host = float(geom.h)
         flags = self.plan_flags | (_lib.WT_F_FORCE_STREAM if tab["force_stream"] else 0)
         spec = LoopSpec(src_ij=tab["src_ij"], prb_ij=tab["prb_ij"], prb_sq=tab["prb_sq"], dt=s["dt"], h=geom._h_host,
-                        b0=s["b0"], uth=s["uth"], c_nl=s["c_nl"], output_fields=fields, flags=flags,
+                        b0=s["b0"], uth=s["uth"], c_nl=s["c_nl"], output_fields=fields,
+                        field_every=max(int(field_every), 1), flags=flags,
                         cluster=self.cluster, rows_per_thread=self.rows_per_thread,
                         checkpoint_every=self.checkpoint_every, batch_chunk=self.batch_chunk)
         y = wave_rnn(x, c, b, rho, spec)
