@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       }
     }
     stage_seeds((a.T - 1) / TB);
+    if ((a.T - 1) / TB > 0) stage_seeds((a.T - 1) / TB - 1);
     __syncthreads();
 
     // One reverse step; PAR = it & 1 is a compile-time constant of each of the two unrolled copies.
@@ -328,8 +329,6 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       constexpr int PAR = decltype(par)::value;
       const int blk = t / TB, tt = t - blk * TB;
       float* cur = fld + PAR * L.slab;
-      if ((t == a.T - 1 || tt == TB - 1) && blk > 0) stage_seeds(blk - 1);
-      if (GRADX && a.grad_x && tt == TB - 1 && t != a.T - 1) flush_gx(blk + 1);
       const unsigned gi = it_global + it;
       const unsigned slot = gi & rg_mask, parity = (gi >> rg_shift) & 1u;
       const unsigned slot2 = (gi + 1) & rg_mask, parity2 = ((gi + 1) >> rg_shift) & 1u;   // stage of step t-1: its u is my u_{t-2}
@@ -424,6 +423,15 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       for (; t >= 1; t -= 2, it += 2) {
         step(P0{}, t, it);
         step(P1{}, t - 1, it + 1);
+        // Per-block staging outside the step bodies.  A block's seeds are read from its first (highest) step on, so the
+        // seeds of the NEXT block are staged after the pair that contains that first step: the half they overwrite
+        // belonged to the block that has just ended.
+        const int tb = ((t & (TB - 1)) == TB - 1) ? t : ((((t - 1) & (TB - 1)) == TB - 1) ? t - 1 : -1);
+        if (tb >= TB && tb != a.T - 1) stage_seeds(tb / TB - 1);
+        if (GRADX && a.grad_x) {
+          if ((t & (TB - 1)) == 0 && t >= TB) flush_gx(t / TB);
+          if (((t - 1) & (TB - 1)) == 0 && t - 1 >= TB) flush_gx((t - 1) / TB);
+        }
       }
       if (t == 0) step(P0{}, 0, it);
     }
