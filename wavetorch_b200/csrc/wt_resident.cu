@@ -4,13 +4,17 @@
 // owns a patch of R rows x 4 columns and keeps, in registers for the whole loop, the two time levels of its
 // cells (u_t, u_{t-1}) and their coefficients.  Shared memory only carries what neighbours need: the current
 // field of the slab (double buffered, with one ghost row per side).  Ghost rows are written straight into
-// the neighbouring CTA's shared memory (DSMEM) and the per-step barrier is the cluster barrier.
+// the neighbouring CTA's shared memory (st.async over DSMEM, completion counted on an mbarrier there, see
+// wt_resident_dev.cuh); inside a CTA there is one __syncthreads() per step and no cluster-wide barrier.
 // HBM is touched only for x[b,t], the probe samples, and -- when a gradient is wanted -- the adjoint tape.
 //
 // Forward  : u_{t}   = u_{t-2} + a1*(u_{t-1}-u_{t-2}) + a3*L(u_{t-1}) ; += x[b,t] at sources ; probes read
-// Adjoint  : lam_{t-1} = a1*lam_t + L(a3*lam_t) + (1-a1)*lam_{t+1} + seed_{t-1};  G += L(u_{t-1})*lam_t
+// Adjoint  : lam_{t-1} = a1*lam_t + L(a3*lam_t) + (1-a1)*lam_{t+1} + seed_{t-1};  G += L(u_{t-1})*lam_t, carried as
+//            P = a3*lam, which obeys the forward update (see k_res_adj)
 //            (the tape holds L(u_{t-1}) per step in the thread-major order the adjoint reads it back in,
 //             fetched by cp.async.bulk into a shared-memory ring ahead of use)
+// The step bodies are kept small on purpose: they are fetched 2T times per sample and everything inlined into them --
+// also code that a branch skips -- costs instruction-cache bandwidth.
 //
 // Reference semantics: wavetorch/rnn.py:36-70, cell.py:12-17, cell.py:27-44, operators.py:5-11,
 // source.py:15-22, probe.py:14-27.
