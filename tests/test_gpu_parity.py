@@ -728,3 +728,31 @@ def test_time_decimated_field_snapshots(path, flags, b0, uth, cnl):
     assert torch.equal(one, full)
     with pytest.raises(NotImplementedError):
         m(x, output_fields=True, field_every=k)
+
+
+@pytest.mark.parametrize("want_xgrad", [False, True])
+@pytest.mark.parametrize("b0,uth,cnl", [(0.0, 0.0, 0.0), (0.1, 1.0, 0.0), (0.0, 1.0, -30.0), (0.1, 1.0, -30.0)])
+def test_shape_specialised_kernels_match_generic_ones(b0, uth, cnl, want_xgrad, monkeypatch):
+    """The on-chip kernels instantiated with compile-time pitch / thread count for the BASELINE config-3/4 shapes (and with
+    the dLoss/dx code compiled out when x.grad is not requested) compute bit-for-bit what the generic instantiations do.
+    B = 64 so that the planner picks the decompositions those instances exist for (C=2,R=5 linear; C=4,R=2 nonlinear)."""
+    B, T = 64, 130
+    x0 = wo.synthetic_vowels(B, T)
+    if cnl != 0.0:
+        x0 = 0.05 * x0          # keep the Kerr term in its stable range
+    w = torch.tensor(np.random.RandomState(7).rand(B, T, 3), dtype=torch.float32, device=DEV)
+    res = []
+    for nospec in ("1", "0"):
+        monkeypatch.setenv("WT_RES_NOSPEC", nospec)
+        m = _vowel_model(b0, uth, cnl)
+        x = torch.tensor(x0, device=DEV, requires_grad=want_xgrad)
+        out = m(x)
+        (out * w).sum().backward()
+        res.append((out.detach().clone(), m.cell.geom.rho.grad.clone(), x.grad.clone() if want_xgrad else None))
+    p = _lib.make_problem(150, 100, B, T, 1, 3, 1.0, 1.4283556979968262, b0, uth, cnl, _lib.WT_F_ZERO_INIT)
+    plan = _lib.query_plan(p)
+    assert (plan.cluster, plan.rows_per_thread) == ((2, 5) if (b0 == 0 and cnl == 0) else (4, 2))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
+    if want_xgrad:
+        assert torch.equal(res[0][2], res[1][2])
