@@ -213,6 +213,23 @@ def test_config3_4_vowel(name, b0, uth, cnl):
         assert rel_l2(x.grad.cpu().numpy(), g["x_grad_f32"]) < 1e-4
 
 
+@pytest.mark.parametrize("name,b0,uth,cnl", VOWEL)
+def test_config3_4_vowel_in_the_bench_decomposition(name, b0, uth, cnl):
+    """The same fixtures with the decomposition forced to the one the planner picks at B=64 (C=2,R=5 linear; C=4,R=2
+    nonlinear), i.e. through the shape-specialised kernels that bench.py and tools/time_configs.py time."""
+    g = load_golden(name)
+    m = _vowel_model(b0, uth, cnl)
+    m.plan_flags = _lib.WT_F_FORCE_RESIDENT
+    m.cluster, m.rows_per_thread = (2, 5) if name == "vowel_linear" else (4, 2)
+    x = torch.tensor(g["x_f64"], dtype=torch.float32, device=DEV)
+    out = m(x)
+    loss = _loss_head(out, torch.arange(6, device=DEV) % 3)
+    loss.backward()
+    floor_o, floor_g = rel_l2(g["out_f32"], g["out_f64"]), rel_l2(g["rho_grad_f32"], g["rho_grad_f64"])
+    assert rel_l2(out.detach().cpu().numpy(), g["out_f64"]) < max(1e-5, 3 * floor_o)
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f64"]) < max(1e-4, 3 * floor_g)
+
+
 # ------------------------------------------------------------------------------------------------
 # full-size properties (BASELINE config 3 size: 150x100, B=64, T=1000)
 # ------------------------------------------------------------------------------------------------
