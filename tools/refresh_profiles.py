@@ -11,7 +11,7 @@ def last_json_line(path):
     return lines[-1]
 
 
-for name in ("bench_n1", "bench_reference_n1", "bench_large_n1", "bench_n2", "bench_large_n2", "bench_n4"):
+for name in ("bench_n1", "bench_reference_n1", "bench_large_n1", "bench_n2", "bench_large_n2", "bench_n4", "bench_n8"):
     src = os.path.join(G, name + ".json")
     if os.path.exists(src):
         with open(os.path.join(P, "r1_" + name + ".json"), "w") as f:
@@ -78,7 +78,7 @@ if os.path.exists(os.path.join(G, "configs.md")):
     t.append("Roofline reference (SURVEY 8d, measured HBM copy peak 6553.9 GB/s): 546 Gcell/s forward (12 B/update), 205 Gcell/s fwd+bwd (32 B/update); the 60 % target is 328 / 123.")
     dref = json.load(open(os.path.join(P, "r1_bench_reference_n1.json")))
     line = f"bench.py (CUDA-graph replay of the whole training iteration, config 3): {d['value']:.1f} Gcell/s on 1 GPU (profiles/r1_bench_n1.json; e2e from pinned host memory {d['e2e']['value']:.1f})"
-    for n in (2, 4):
+    for n in (2, 4, 8):
         pn = os.path.join(P, f"r1_bench_n{n}.json")
         if os.path.exists(pn):
             line += f", {json.load(open(pn))['value']:.1f} on {n} GPUs"
