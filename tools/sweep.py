@@ -1,5 +1,5 @@
 """Time the on-chip kernels over (cluster, rows_per_thread) decompositions.  Usage: python tools/sweep.py [B] [T]"""
-import sys, os, itertools
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch

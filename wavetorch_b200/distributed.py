@@ -102,7 +102,6 @@ class BatchShardedWaveRNN(torch.nn.Module):
                 self.reducer, self.reduce_mode = None, "all_reduce"
 
     def forward(self, x_local, output_fields=False):
-        from .functional import LoopSpec, wave_rnn  # noqa: F401
         m = self.model
         geom = m.cell.geom
         c, rho, b = geom.c, geom.rho, geom.b

@@ -35,7 +35,6 @@ class _FusedSpeed(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rho, taps, eta, beta, c0, c1, passes):
-        import ctypes
         from . import _lib
         lib = _lib.load()
         dev = rho.device

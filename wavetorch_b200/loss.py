@@ -9,8 +9,6 @@ Drop-in for the two lines every training/eval pass of the reference runs on the 
 `power_cross_entropy(out, labels)` returns `(loss, yb_pred)` from one kernel launch (`wt_loss_forward`); its backward is a
 broadcast of a [B,P] table (`wt_loss_backward`) because dLoss/dout[b,t,p] does not depend on t.
 """
-import ctypes
-
 import torch
 
 from . import _lib
