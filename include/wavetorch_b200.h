@@ -51,6 +51,8 @@ extern "C" {
 #define WT_F_FORCE_STREAM 2u    /* plan: always use the HBM-streaming kernels                             */
 #define WT_F_FORCE_RESIDENT 4u  /* plan: fail with WT_EUNSUPPORTED instead of falling back to streaming  */
 #define WT_F_NEED_GRAD_B 8u     /* the tape must allow grad w.r.t. the damping field in linear mode      */
+#define WT_F_NO_SPECIALIZE 16u  /* on-chip path: run the generic kernels, not a shape-specialised instantiation
+                                   (A/B measurements; results are bitwise identical either way)            */
 
 /* wt_plan.path */
 #define WT_PATH_STREAM 0    /* one launch per time step, fields live in HBM                     */
@@ -63,7 +65,7 @@ typedef struct wt_problem {
   int32_t Nx, Ny;   /* grid */
   int32_t B;        /* independent waveforms (batch) */
   int32_t T;        /* time steps advanced by this call */
-  int32_t n_src;    /* source pixel entries; a pixel listed k times receives k*x (rnn.py:56-57) */
+  int32_t n_src;    /* source pixel entries; a pixel listed k times receives k*x (rnn.py:56-57); see wt_validate_pixels */
   int32_t n_prb;    /* probe pixels */
   uint32_t flags;
   int32_t device;   /* CUDA device ordinal */
@@ -99,6 +101,19 @@ const char* wt_last_error(void);
 
 /* Fill `plan` for `p` on p->device (queries the device; launches nothing). */
 int wt_query_plan(const wt_problem* p, wt_plan* plan);
+
+/*
+ * Host-side check of the pixel lists a caller is about to pass to wt_forward / wt_backward.  src_ij_host / prb_ij_host are
+ * HOST copies ([n_src,2] / [n_prb,2], (row, col)) of the device arrays.  Returns WT_EINVAL when a coordinate lies outside
+ * the p->Nx x p->Ny grid; otherwise WT_OK with *max_listings (nullable) = the largest number of times one source pixel
+ * is listed (0 without sources).  wt_forward / wt_backward only see device pointers and cannot check them without a
+ * synchronisation, so this is the caller's contract: coordinates must be in range (the kernels redirect an out-of-range
+ * entry to cell (0,0) rather than touch foreign memory), and a problem whose *max_listings exceeds WT_MAX_SRC_LISTINGS
+ * must set WT_F_FORCE_STREAM -- the on-chip kernels add x[b,t] at most that many times per pixel (rnn.py:56-57 adds it
+ * once per listing; the streaming kernels handle any count).
+ */
+#define WT_MAX_SRC_LISTINGS 3
+int wt_validate_pixels(const wt_problem* p, const int32_t* src_ij_host, const int32_t* prb_ij_host, int32_t* max_listings);
 
 /*
  * Advance p->T steps for p->B waveforms.
@@ -143,6 +158,53 @@ int wt_backward(const wt_problem* p, const float* c, const float* b, const float
                 const void* history, size_t history_bytes, float* adj1, float* adj2, float* grad_c,
                 float* grad_b, float* grad_rho, float* grad_x, void* workspace, size_t workspace_bytes,
                 void* stream);
+
+/*
+ * Row-slab domain decomposition of ONE simulation over the GPUs of a box (BASELINE config 5; the reference has no
+ * counterpart).  Every rank runs wt_slab_forward / wt_slab_backward on ITS slab: p->Nx counts the rows it owns plus
+ * `halo` ghost rows on each side that borders another rank.  The slab is integrated as an isolated domain for `halo`
+ * steps (the error made at its artificial edges moves inwards one row per step, so the owned rows stay exact); then
+ * neighbours refresh each other's ghost rows IN THE SAME STREAM, WITHOUT THE HOST: one kernel per exchange stores the
+ * `halo` owned rows next to each interior edge, both time levels, straight into the neighbour's ghost rows through
+ * NVLink peer-mapped pointers, and synchronises with the neighbours through flag words (st.release.sys / ld.acquire.sys).
+ * An exchange also closes every call, so consecutive calls (checkpoint segments) chain without further communication.
+ *
+ *   halo        steps between exchanges = ghost rows per interior side; a multiple of 8
+ *   up, dn      ghost rows above / below my owned rows: 0 at the domain edge, else halo
+ *   up_f1/up_f2 address IN THIS PROCESS of the UPPER neighbour's copies of the two state fields the call advances
+ *               (u1/u2 for wt_slab_forward, adj1/adj2 for wt_slab_backward), [B, up_Nx, Ny]; dn_*: the lower neighbour's
+ *   up_flags, dn_flags   address in this process of the neighbours' flag words (uint32[4], zero before the first call)
+ *   flags       my own flag words (same layout: {ready, pushed} written by the upper neighbour, then by the lower one)
+ *   state       my own uint32[2], zero before the first call (exchange epoch, block counter)
+ * All ranks must issue the same sequence of calls.  The peer mappings come from the caller (cudaIpc / VMM / torch
+ * symmetric memory: wavetorch_b200/domain.py); several slabs of one process may also exchange through plain device
+ * pointers when each runs on its own stream.  Saturable damping / Kerr terms: forward only (WT_EUNSUPPORTED in
+ * wt_slab_backward: the local adjoint coefficients would depend on the inexact ghost fields).
+ * The other arguments are those of wt_forward / wt_backward for the local slab (coordinates relative to its first row);
+ * u1/u2 resp. adj1/adj2 are required and must be the buffers the neighbours have mapped.
+ */
+typedef struct wt_slab {
+  int32_t halo, up, dn;
+  int32_t up_Nx, dn_Nx;     /* rows of the neighbours' slabs */
+  int32_t reserved[3];
+  uint64_t up_f1, up_f2, dn_f1, dn_f2;
+  uint64_t up_flags, dn_flags;
+  uint32_t* flags;
+  uint32_t* state;
+} wt_slab;
+
+int wt_slab_forward(const wt_problem* p, const wt_slab* slab, const float* c, const float* b, const float* rho,
+                    const float* x, const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, float* u1,
+                    float* u2, float* probe_out, float* probe_raw, void* history, size_t history_bytes, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+int wt_slab_backward(const wt_problem* p, const wt_slab* slab, const float* c, const float* b, const float* rho,
+                     const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, const float* grad_probe,
+                     const float* probe_raw, const void* history, size_t history_bytes, float* adj1, float* adj2,
+                     float* grad_c, float* grad_x, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The exchange on its own (both fields of a [B,Nx,Ny] pair), e.g. to refresh ghost rows after loading a checkpoint. */
+int wt_slab_exchange(const wt_slab* slab, int B, int Nx, int Ny, float* f1, float* f2, int device, void* stream);
 
 /*
  * One leapfrog step without sources or probes: y = TimeStep.apply(b, c, y1, y2, dt, h).

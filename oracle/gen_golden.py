@@ -116,6 +116,34 @@ def vowel_case(name, B, T, b0, uth, cnl, x_grad=False):
     print(name, float(res["loss_f32"]), float(res["loss_f64"]), float(np.linalg.norm(res["rho_grad_f64"])))
 
 
+def vowel_sums_case(name, B, T):
+    """Full BASELINE config-3 batch (B=64, T=1000), forward only: the per-sample probe energies sum_t I the loss head
+    consumes (train.py:61), float32 and float64.  64x3 numbers pin the full-size run of the CUDA path."""
+    sys.path.insert(0, "/root/reference/study")
+    from vowel_helpers import setup_src_coords, setup_probe_coords
+    res = {}
+    Nx, Ny, N = 150, 100, 20
+    for dname in ("float32", "float64"):
+        tdt, ndt = _dtype(dname)
+        probes = setup_probe_coords(3, None, None, 20, Nx, Ny, N)
+        source = setup_src_coords(None, None, Nx, Ny, N)
+        design_region = torch.zeros(Nx, Ny, dtype=torch.uint8)
+        design_region[source[0].x.item() + 5:probes[0].x.item() - 5] = 1
+        geom = wt.WaveGeometryFreeForm((Nx, Ny), 1.4283556979968262, c0=1.0, c1=0.5, eta=0.5, beta=100,
+                                       abs_sig=3.0, abs_N=N, abs_p=4.0, rho="half", blur_radius=1, blur_N=1,
+                                       design_region=design_region)
+        model = wt.WaveRNN(wt.WaveCell(1.0, geom), source, probes)
+        X = torch.tensor(wo.synthetic_vowels(B, T, dtype=np.float64), dtype=tdt)
+        with torch.no_grad():
+            out = model(X)
+        sfx = "_f32" if dname == "float32" else "_f64"
+        res["sums" + sfx] = _np(out.sum(dim=1))
+        res["out_last" + sfx] = _np(out[:, -1])
+    res["BT"] = np.array([B, T])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **res)
+    print(name, res["sums_f32"][:2], res["sums_f64"][:2])
+
+
 def small_case(name, b0, uth, cnl, seed, xamp=0.3):
     """Small irregular grid: mixed plain/intensity probes, two sources sharing one pixel (SURVEY B-3),
     x.grad, final fields.  Loss = weighted sum of outputs (weights stored)."""
@@ -303,6 +331,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":      # regenerate only the training-loop fixture
         train_case("train_small")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":     # the fixtures added in round 2 only
+        vowel_sums_case("vowel_linear_B64_sums", 64, 1000)
+        vowel_case("vowel_satdamp_T3000", 3, 3000, 0.1, 1.0, 0.0)   # config 4 at the yml's window_size (example_nonlinearity.yml:38)
+        sys.exit(0)
     single_step_case("single_step")
     geometry_case("geometry")
     state_dict_case("state_dict")
@@ -317,4 +349,6 @@ if __name__ == "__main__":
     vowel_case("vowel_both", 6, 1000, 0.1, 1.0, -30.0)       # config 4 (ii)
     vowel_case("vowel_satdamp_uth", 6, 1000, 0.1, 0.00018, 0.0)  # config 4 (iii)
     vowel_case("vowel_kerr", 6, 1000, 0.0, 1.0, -30.0)
+    vowel_sums_case("vowel_linear_B64_sums", 64, 1000)
+    vowel_case("vowel_satdamp_T3000", 3, 3000, 0.1, 1.0, 0.0)
     train_case("train_small")

@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  This file is used by `oracle/gen_golden.py` (and by ad-hoc
 validation in the build container) to run the real fancompute/wavetorch CPU path.
-/root/reference does not exist on the GPU box, so nothing under tests/ -m gpu, bench.py or
-__graft_entry__.smoke() imports this module.
+/root/reference does not exist on the GPU box; there the only copy of the reference is the pip-installed one under
+baseline/_ref/ (see DESIGN.md section 5), which `bench.py --impl reference` (and only that arm) loads through this
+module.  Nothing under tests/ -m gpu, the product arm of bench.py or __graft_entry__.smoke() imports it.
 
 `import wavetorch` fails out of the box because wavetorch/__init__.py:1 pulls in
 skimage (geom.py:7, source.py:1), librosa (data/vowels.py:6), matplotlib/seaborn (plot.py:6-11),
@@ -15,12 +16,14 @@ none of which is installed here.  The two functions that matter numerically are 
 * skimage.draw.line(r0, c0, r1, c1)  -- Bresenham, end points inclusive (source.py:31).
 """
 import importlib
+import os
 import sys
 import types
 
 import numpy as np
 
 REFERENCE_ROOT = "/root/reference"
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
 def _disk(r, c, radius, shape=None):
@@ -86,11 +89,28 @@ def _install_stubs():
     sys.modules["librosa"].display = sys.modules["librosa.display"]
 
 
-def load_reference():
+def reference_root(prefer_installed=False):
+    """Directory holding the reference package: the source tree (build container) or the pip-installed copy under
+    baseline/_ref (the only one that exists on the GPU box); None when neither is there."""
+    roots = (INSTALLED_ROOT, REFERENCE_ROOT) if prefer_installed else (REFERENCE_ROOT, INSTALLED_ROOT)
+    for r in roots:
+        if os.path.isfile(os.path.join(r, "wavetorch", "rnn.py")):
+            return r
+    return None
+
+
+def load_reference(root=None):
     """Return the reference `wavetorch` module (real code, stubbed third-party deps)."""
     _install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = root or reference_root()
+    if root is None:
+        raise ImportError("no copy of the reference: neither %s nor %s exists" % (REFERENCE_ROOT, INSTALLED_ROOT))
+    if not os.path.isdir(os.path.join(root, "wavetorch", "data")) and "wavetorch.data" not in sys.modules:
+        # the reference's setup.py lists packages=['wavetorch'] only, so a pip install drops the wavetorch.data
+        # sub-package that wavetorch/__init__.py:1 imports (the librosa vowel loader: out of scope here)
+        sys.modules["wavetorch.data"] = types.ModuleType("wavetorch.data")
+    if root not in sys.path:
+        sys.path.insert(0, root)
     return importlib.import_module("wavetorch")
 
 

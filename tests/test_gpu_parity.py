@@ -5,6 +5,8 @@ Tolerances (relative L2 unless stated), from BASELINE.json north_star / SURVEY.m
   probe outputs 1e-5 vs the float32 reference (3e-5 on config 2 whose side probes sit at the reference's own
   float32 noise floor), rho-gradients 1e-4; saturable-damping cases max(tol, 3*|ref32-ref64|).
 """
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -423,20 +425,32 @@ def test_config5_truncated_large_grid_against_oracle():
     assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), grho) < 1e-4
 
 
-@pytest.mark.parametrize("b0,uth,cnl", [(0.0, 0.0, 0.0), (0.3, 0.7, -0.1)])
-@pytest.mark.parametrize("nslabs,halo", [(2, 8), (3, 5), (4, 12)])
-def test_domain_decomposition_virtual_ranks(b0, uth, cnl, nslabs, halo):
-    """Row-slab domain decomposition with halo depth = temporal block, all slabs in one process:
-    identical probe series, rho.grad and x.grad as the undecomposed run."""
-    from wavetorch_b200.domain import DomainDecomposedWaveRNN
-    Nx, Ny, B, T, N = 96, 72, 2, 61, 6
-    rng = np.random.RandomState(3)
-    rho0 = rng.rand(Nx, Ny).astype(np.float32)
+def _dd_models(Nx, Ny, N, rho0, b0=0.0, uth=0.0, cnl=0.0):
     def build():
         geom = wt.WaveGeometryFreeForm((Nx, Ny), 1.0, 1.0, 0.6, abs_N=N, abs_sig=3.0, abs_p=3.0, beta=10.0, rho=torch.tensor(rho0))
-        src = [wt.WaveSource(N + 4, Ny // 2), wt.WaveSource(47, 20)]
-        prb = [wt.WaveIntensityProbe(Nx - N - 4, 20), wt.WaveProbe(48, 50), wt.WaveIntensityProbe(23, 40), wt.WaveProbe(71, 30)]
+        src = [wt.WaveSource(N + 4, Ny // 2), wt.WaveSource(Nx // 2 - 1, 20)]
+        prb = [wt.WaveIntensityProbe(Nx - N - 4, 20), wt.WaveProbe(Nx // 2, 50), wt.WaveIntensityProbe(Nx // 4 - 1, 40),
+               wt.WaveProbe(3 * Nx // 4 - 1, 30)]
         return wt.WaveRNN(wt.WaveCell(0.6, geom, satdamp_b0=b0, satdamp_uth=uth, c_nl=cnl), src, prb).to(DEV)
+    return build
+
+
+@pytest.mark.parametrize("tile", [False, True])
+@pytest.mark.parametrize("nslabs,halo,ckpt,chunk", [(2, 8, 0, 0), (3, 8, 16, 0), (4, 16, 24, 0), (2, 16, 32, 2), (4, 8, 8, 1)])
+def test_domain_decomposition_virtual_ranks(nslabs, halo, ckpt, chunk, tile, monkeypatch):
+    """Row-slab domain decomposition with halo depth = temporal block, all slabs in one process, each on its
+    own stream, exchanging ghost rows through the peer-store kernel and flag protocol of csrc/wt_slab.cu: BITWISE the
+    probe series of the undecomposed run, rho.grad and x.grad to summation order.  Checkpoint interval (any multiple of
+    the halo) and batch chunks are independent of the halo.  tile: through the temporally blocked kernels (config 5's)."""
+    from wavetorch_b200.domain import DomainDecomposedWaveRNN
+    if tile:
+        monkeypatch.setenv("WT_TILE_MIN_CELLS", "0")
+    else:
+        monkeypatch.setenv("WT_NO_TILE", "1")
+    Nx, Ny, B, T, N = 96, 72, 3, 61, 6
+    rng = np.random.RandomState(3)
+    rho0 = rng.rand(Nx, Ny).astype(np.float32)
+    build = _dd_models(Nx, Ny, N, rho0)
     x0 = (0.2 * rng.randn(B, T)).astype(np.float32)
     w = torch.tensor(rng.randn(B, T, 4).astype(np.float32), device=DEV)
     ref = build(); ref.plan_flags = _lib.WT_F_FORCE_STREAM
@@ -444,13 +458,58 @@ def test_domain_decomposition_virtual_ranks(b0, uth, cnl, nslabs, halo):
     out_ref = ref(xr)
     (out_ref * w).sum().backward()
     m = build()
-    dd = DomainDecomposedWaveRNN(m, halo=halo, virtual_ranks=nslabs)
-    xd = torch.tensor(x0, device=DEV, requires_grad=True)
-    out = dd(xd)
-    (out * w).sum().backward()
-    assert rel_l2(out.detach().cpu().numpy(), out_ref.detach().cpu().numpy()) < 2e-6
-    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), ref.cell.geom.rho.grad.cpu().numpy()) < 2e-5
-    assert rel_l2(xd.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-5
+    dd = DomainDecomposedWaveRNN(m, halo=halo, virtual_ranks=nslabs, checkpoint_every=ckpt, batch_chunk=chunk)
+    for it in range(2):      # second pass: the cached context (state buffers, flags, epoch) is reused
+        m.zero_grad()
+        xd = torch.tensor(x0, device=DEV, requires_grad=True)
+        out = dd(xd)
+        (out * w).sum().backward()
+        assert torch.equal(out.detach(), out_ref.detach())
+        assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), ref.cell.geom.rho.grad.cpu().numpy()) < 2e-5
+        assert rel_l2(xd.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 2e-5
+    assert dd.exchange_bytes == 2 * halo * Ny * (chunk or B) * 4
+
+
+def test_domain_decomposition_nonlinear_forward_only():
+    """Saturable damping + Kerr under the decomposition: the forward is exact (bitwise the undecomposed run); the
+    adjoint is refused (its local coefficients would come from inexact ghost fields -- ADVICE round 1)."""
+    from wavetorch_b200.domain import DomainDecomposedWaveRNN
+    Nx, Ny, B, T, N = 96, 72, 2, 45, 6
+    rng = np.random.RandomState(4)
+    rho0 = rng.rand(Nx, Ny).astype(np.float32)
+    build = _dd_models(Nx, Ny, N, rho0, 0.3, 0.7, -0.1)
+    x = torch.tensor((0.2 * rng.randn(B, T)).astype(np.float32), device=DEV)
+    ref = build(); ref.plan_flags = _lib.WT_F_FORCE_STREAM
+    dd = DomainDecomposedWaveRNN(build(), halo=8, virtual_ranks=3)
+    with torch.no_grad():
+        assert torch.equal(dd(x), ref(x))
+    with pytest.raises(NotImplementedError, match="linear cell only"):
+        dd(x)
+
+
+def test_domain_decomposition_large_grid_bitwise():
+    """A config-5-like window (1024 x 1024, blocked kernels chosen by the planner, 4 slabs): probes bitwise equal to the
+    single-slab run with the same checkpoints -- every cell sees the same arithmetic in either layout -- and rho.grad to
+    the order in which the blocked adjoint's batch chunks add their partial sums (atomics at this small batch)."""
+    from wavetorch_b200.domain import DomainDecomposedWaveRNN
+    N, B, T = 1024, 4, 48
+    import math
+    ii = torch.arange(N, dtype=torch.float32)[:, None]; jj = torch.arange(N, dtype=torch.float32)[None, :]
+    rho = 0.5 + 0.5 * torch.sin(2 * math.pi * ii / 97) * torch.cos(2 * math.pi * jj / 61)
+    def build():
+        geom = wt.WaveGeometryFreeForm((N, N), 1.4283556979968262, 1.0, 0.5, abs_N=20, abs_sig=3.0, abs_p=4.0, rho=rho)
+        probes = [wt.WaveIntensityProbe(N // 2 + 10, N // 2 + 6 * k) for k in (-1, 0, 1)]
+        return wt.WaveRNN(wt.WaveCell(1.0, geom), [wt.WaveSource(N // 2 - 10, N // 2)], probes).to(DEV)
+    torch.manual_seed(0)
+    x = (0.1 * torch.randn(B, T)).to(DEV)
+    w = torch.randn(B, T, 3).to(DEV)
+    ref = build(); ref.plan_flags = _lib.WT_F_FORCE_STREAM; ref.checkpoint_every = 16
+    o1 = ref(x); (o1 * w).sum().backward()
+    m = build()
+    dd = DomainDecomposedWaveRNN(m, halo=16, virtual_ranks=4, checkpoint_every=16)
+    o2 = dd(x); (o2 * w).sum().backward()
+    assert torch.equal(o1.detach(), o2.detach())
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), ref.cell.geom.rho.grad.cpu().numpy()) < 1e-6
 
 
 @pytest.mark.parametrize("ckpt", [0, 16])
@@ -773,3 +832,135 @@ def test_shape_specialised_kernels_match_generic_ones(b0, uth, cnl, want_xgrad, 
     assert torch.equal(res[0][1], res[1][1])
     if want_xgrad:
         assert torch.equal(res[0][2], res[1][2])
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2 additions
+# ------------------------------------------------------------------------------------------------
+def test_config3_full_batch_sums_against_reference():
+    """BASELINE config 3 at its full size (B=64, T=1000): the 64x3 probe energies sum_t I -- what the loss head consumes --
+    against the unmodified reference's float32 and float64 runs (fixture vowel_linear_B64_sums)."""
+    g = load_golden("vowel_linear_B64_sums")
+    m = _vowel_model()
+    x = torch.tensor(wo.synthetic_vowels(64, 1000), device=DEV)
+    with torch.no_grad():
+        out = m(x)
+    S = out.sum(dim=1).cpu().numpy()
+    assert rel_l2(S, g["sums_f32"]) < 1e-5
+    assert rel_l2(S, g["sums_f64"]) < 1e-5
+    assert rel_l2(out[:, -1].cpu().numpy(), g["out_last_f64"]) < 1e-5
+
+
+@pytest.mark.parametrize("path,flags", PATHS)
+def test_config4_T3000(path, flags):
+    """BASELINE config 4 at the yml's own window_size = 3000 (study/example_nonlinearity.yml:38): saturable damping
+    b0 = 0.1, uth = 1.0; B = 3.  The on-chip tape ring wraps 750 times; tolerance max(tol, 3*|ref32 - ref64|)."""
+    g = load_golden("vowel_satdamp_T3000")
+    m = _vowel_model(0.1, 1.0, 0.0)
+    m.plan_flags = flags
+    x = torch.tensor(g["x_f64"], dtype=torch.float32, device=DEV)
+    out = m(x)
+    loss = _loss_head(out, torch.arange(3, device=DEV) % 3)
+    loss.backward()
+    floor_o, floor_g = rel_l2(g["out_f32"], g["out_f64"]), rel_l2(g["rho_grad_f32"], g["rho_grad_f64"])
+    assert out.shape == (3, 3000, 3)
+    assert rel_l2(out.detach().cpu().numpy(), g["out_f64"]) < max(1e-5, 3 * floor_o)
+    assert abs(loss.item() - float(g["loss_f64"])) < 5e-6
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f64"]) < max(1e-4, 3 * floor_g)
+
+
+@pytest.mark.parametrize("path,flags", PATHS + [("tile", _lib.WT_F_FORCE_STREAM)])
+def test_zero_wave_speed_cell(path, flags, monkeypatch):
+    """A cell with c == 0 (cell.py:36: dLoss/dc is proportional to c there, i.e. exactly 0): the adjoint kernels carry
+    a3*lambda, which vanishes at such a cell -- the gradient must come out 0 there (not 0/0) and be unaffected elsewhere."""
+    if path == "tile":
+        monkeypatch.setenv("WT_TILE_MIN_CELLS", "0")
+    elif path == "stream":
+        monkeypatch.setenv("WT_NO_TILE", "1")
+    lib = _lib.load()
+    Nx, Ny, B, T = 40, 36, 2, 50
+    rng = np.random.RandomState(9)
+    c = (0.6 + 0.4 * rng.rand(Nx, Ny))
+    c[17, 20] = 0.0
+    c[25, 9] = 0.0
+    b = wo.pml_damping(Nx, Ny, 5, 3.0, 4.0, np.float64)
+    x = 0.3 * rng.randn(B, T)
+    w = rng.randn(B, T, 2)
+    src, prb, sq = np.array([[8, 18]]), np.array([[30, 10], [28, 25]]), np.array([True, False])
+    f = wo.forward(c, b, np.zeros_like(c), x, src, prb, 0.5, 1.0, keep_fields=True)
+    a = wo.adjoint(c, b, np.zeros_like(c), x, src, prb, sq, 0.5, 1.0, w, f)
+    assert a["grad_c"][17, 20] == 0.0 and np.isfinite(a["grad_c"]).all()
+    # straight through the C ABI: c is an input there (the geometry classes never produce c == 0)
+    t = lambda v, dt=torch.float32: torch.tensor(np.asarray(v), dtype=dt, device=DEV).contiguous()
+    p = _lib.make_problem(Nx, Ny, B, T, 1, 2, 0.5, 1.0, flags=flags | _lib.WT_F_ZERO_INIT)
+    plan = _lib.query_plan(p)
+    c32, b32, x32 = t(c), t(b), t(x)
+    sij, pij, psq = t(src, torch.int32), t(prb, torch.int32), t(sq.astype(np.int32), torch.int32)
+    u1, u2 = torch.empty(B, Nx, Ny, device=DEV), torch.empty(B, Nx, Ny, device=DEV)
+    po, pr = torch.empty(B, T, 2, device=DEV), torch.empty(B, T, 2, device=DEV)
+    ws = torch.empty(max(int(plan.workspace_fwd_bytes), int(plan.workspace_bwd_bytes), 16), dtype=torch.uint8, device=DEV)
+    hist = torch.empty(max(int(plan.history_bytes), 16), dtype=torch.uint8, device=DEV)
+    st = lib.wt_forward(ctypes.byref(p), _lib.ptr(c32), _lib.ptr(b32), None, _lib.ptr(x32), _lib.ptr(sij), _lib.ptr(pij),
+                        _lib.ptr(psq), _lib.ptr(u1), _lib.ptr(u2), _lib.ptr(po), _lib.ptr(pr), None, _lib.ptr(hist),
+                        hist.numel(), _lib.ptr(ws), ws.numel(), None)
+    _lib.check(st, "wt_forward")
+    gc, gx = torch.empty(Nx, Ny, device=DEV), torch.empty(B, T, device=DEV)
+    st = lib.wt_backward(ctypes.byref(p), _lib.ptr(c32), _lib.ptr(b32), None, _lib.ptr(sij), _lib.ptr(pij), _lib.ptr(psq),
+                         _lib.ptr(t(w)), _lib.ptr(pr), None, _lib.ptr(hist), hist.numel(), None, None, _lib.ptr(gc), None,
+                         None, _lib.ptr(gx), _lib.ptr(ws), ws.numel(), None)
+    _lib.check(st, "wt_backward")
+    torch.cuda.synchronize()
+    assert rel_l2(po.cpu().numpy(), wo.probe_outputs(f["raw"], sq)) < 1e-5
+    gcn = gc.cpu().numpy()
+    assert np.isfinite(gcn).all() and gcn[17, 20] == 0.0 and gcn[25, 9] == 0.0
+    assert rel_l2(gcn, a["grad_c"]) < 1e-4
+    assert rel_l2(gx.cpu().numpy(), a["grad_x"]) < 1e-4
+
+
+def test_validate_pixels_and_triple_listing():
+    """wt_validate_pixels (host-side contract check of the C ABI) and a source pixel listed three times on the on-chip
+    path (rnn.py:56-57 adds x once per listing)."""
+    lib = _lib.load()
+    src = torch.tensor([[5, 5], [5, 5], [9, 2], [5, 5], [5, 5]], dtype=torch.int32)
+    prb = torch.tensor([[1, 1]], dtype=torch.int32)
+    assert _lib.validate_pixels(20, 20, src, prb) == 4
+    with pytest.raises(IndexError, match="outside"):
+        _lib.validate_pixels(20, 20, torch.tensor([[20, 0]], dtype=torch.int32), prb)
+    with pytest.raises(IndexError, match="outside"):
+        _lib.validate_pixels(20, 20, src, torch.tensor([[0, -1]], dtype=torch.int32))
+    # three listings of one pixel: on-chip kernels == streaming kernels == 3x a single listing of a linear problem
+    def run(n_list, flags):
+        geom = wt.WaveGeometryFreeForm((48, 40), 1.0, 1.0, 0.5, abs_N=5, abs_sig=3.0, abs_p=4.0, beta=20.0,
+                                       rho=torch.tensor(np.random.RandomState(0).rand(48, 40).astype(np.float32)))
+        m = wt.WaveRNN(wt.WaveCell(0.5, geom), [wt.WaveSource(10, 20) for _ in range(n_list)],
+                       [wt.WaveProbe(38, 12), wt.WaveIntensityProbe(30, 28)]).to(DEV)
+        m.plan_flags = flags
+        x = torch.tensor(0.3 * np.random.RandomState(1).randn(2, 40).astype(np.float32), device=DEV, requires_grad=True)
+        out = m(x)
+        out.sum().backward()
+        return out.detach(), m.cell.geom.rho.grad.clone(), x.grad.clone()
+    o3, g3, x3 = run(3, _lib.WT_F_FORCE_RESIDENT)
+    s3, gs3, xs3 = run(3, _lib.WT_F_FORCE_STREAM)
+    assert rel_l2(o3.cpu().numpy(), s3.cpu().numpy()) < 1e-6
+    assert rel_l2(g3.cpu().numpy(), gs3.cpu().numpy()) < 1e-5
+    assert rel_l2(x3.cpu().numpy(), xs3.cpu().numpy()) < 1e-5
+    o4, _, _ = run(4, 0)        # four listings: the binding routes the model to the streaming kernels
+    s4, _, _ = run(4, _lib.WT_F_FORCE_STREAM)
+    assert torch.equal(o4, s4)
+
+
+def test_deep_tape_ring_small_batches():
+    """Latency-bound decompositions (small patches) prefetch the adjoint tape 8-16 steps ahead; the ring depth is a plan
+    property: same gradients as the streaming path, and the plan reports it."""
+    p = _lib.make_problem(150, 100, 8, 300, 1, 3, 1.0, 1.4283556979968262, device=0)
+    plan = _lib.query_plan(p)
+    assert plan.path == _lib.WT_PATH_RESIDENT and plan.reserved[0] in (2, 4, 8, 16)
+    m = _vowel_model()
+    x = torch.tensor(wo.synthetic_vowels(8, 300), device=DEV)
+    lab = torch.arange(8, device=DEV) % 3
+    _loss_head(m(x), lab).backward()
+    g1 = m.cell.geom.rho.grad.clone()
+    m.zero_grad()
+    m.plan_flags = _lib.WT_F_FORCE_STREAM
+    _loss_head(m(x), lab).backward()
+    assert rel_l2(g1.cpu().numpy(), m.cell.geom.rho.grad.cpu().numpy()) < 2e-5

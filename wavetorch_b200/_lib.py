@@ -15,12 +15,13 @@ WT_F_ZERO_INIT = 1
 WT_F_FORCE_STREAM = 2
 WT_F_FORCE_RESIDENT = 4
 WT_F_NEED_GRAD_B = 8
+WT_F_NO_SPECIALIZE = 16
 WT_PATH_STREAM = 0
 WT_PATH_RESIDENT = 1
 
-EXPORTS = ("wt_abi_version", "wt_last_error", "wt_query_plan", "wt_forward", "wt_backward", "wt_step_forward",
+EXPORTS = ("wt_abi_version", "wt_last_error", "wt_query_plan", "wt_validate_pixels", "wt_forward", "wt_backward", "wt_step_forward",
            "wt_step_backward", "wt_geom_forward", "wt_geom_backward", "wt_loss_forward", "wt_loss_backward",
-           "wt_peer_allreduce")
+           "wt_peer_allreduce", "wt_slab_forward", "wt_slab_backward", "wt_slab_exchange")
 
 
 class WtProblem(ctypes.Structure):
@@ -63,6 +64,7 @@ def load():
         lib.wt_abi_version.restype = ctypes.c_int
         lib.wt_last_error.restype = ctypes.c_char_p
         lib.wt_query_plan.argtypes = [ctypes.POINTER(WtProblem), ctypes.POINTER(WtPlan)]
+        lib.wt_validate_pixels.argtypes = [ctypes.POINTER(WtProblem), vp, vp, ctypes.POINTER(ctypes.c_int32)]
         lib.wt_forward.argtypes = [ctypes.POINTER(WtProblem)] + [vp] * 12 + [vp, sz, vp, sz, vp]
         lib.wt_backward.argtypes = [ctypes.POINTER(WtProblem)] + [vp] * 9 + [vp, sz] + [vp] * 6 + [vp, sz, vp]
         lib.wt_step_forward.argtypes = [ctypes.POINTER(WtProblem), vp, i32, vp, i32, vp, vp, vp, vp]
@@ -73,7 +75,12 @@ def load():
         lib.wt_loss_backward.argtypes = [i32, i32, i32] + [vp] * 3 + [i32, vp]
         lib.wt_peer_allreduce.argtypes = [i32, i32, i32, i32, ctypes.c_float, vp, vp, ctypes.POINTER(ctypes.c_uint64),
                                           ctypes.c_uint64, vp, i32, vp]
-        for name in ("wt_query_plan", "wt_forward", "wt_backward", "wt_step_forward", "wt_step_backward",
+        lib.wt_slab_forward.argtypes = [ctypes.POINTER(WtProblem), vp] + [vp] * 11 + [vp, sz, vp, sz, vp]
+        lib.wt_slab_backward.argtypes = [ctypes.POINTER(WtProblem), vp] + [vp] * 8 + [vp, sz] + [vp] * 4 + [vp, sz, vp]
+        lib.wt_slab_exchange.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
+        for name in ("wt_slab_forward", "wt_slab_backward", "wt_slab_exchange"):
+            getattr(lib, name).restype = ctypes.c_int
+        for name in ("wt_query_plan", "wt_validate_pixels", "wt_forward", "wt_backward", "wt_step_forward", "wt_step_backward",
                      "wt_geom_forward", "wt_geom_backward", "wt_loss_forward", "wt_loss_backward",
                      "wt_peer_allreduce"):
             getattr(lib, name).restype = ctypes.c_int
@@ -105,6 +112,8 @@ def make_problem(Nx, Ny, B, T, n_src, n_prb, dt, h, b0=0.0, uth=0.0, c_nl=0.0, f
                  rows_per_thread=0):
     p = WtProblem()
     p.Nx, p.Ny, p.B, p.T, p.n_src, p.n_prb = int(Nx), int(Ny), int(B), int(T), int(n_src), int(n_prb)
+    if os.environ.get("WT_RES_NOSPEC", "0") == "1":     # A/B switch: generic instead of shape-specialised kernels
+        flags |= WT_F_NO_SPECIALIZE
     p.flags, p.device = int(flags), int(device)
     p.dt, p.h, p.b0, p.uth, p.c_nl = float(dt), float(h), float(b0), float(uth), float(c_nl)
     p.cluster = int(os.environ.get("WT_CLUSTER", cluster))
@@ -116,6 +125,23 @@ def query_plan(problem):
     plan = WtPlan()
     check(load().wt_query_plan(ctypes.byref(problem), ctypes.byref(plan)), "wt_query_plan")
     return plan
+
+
+WT_MAX_SRC_LISTINGS = 3
+
+
+def validate_pixels(Nx, Ny, src_ij_host, prb_ij_host):
+    """wt_validate_pixels on HOST int32 tensors [n,2]: raises on out-of-range coordinates, returns the largest number of
+    listings of one source pixel."""
+    p = make_problem(Nx, Ny, 1, 1, src_ij_host.shape[0], prb_ij_host.shape[0], 1.0, 1.0)
+    s = src_ij_host.contiguous()
+    q = prb_ij_host.contiguous()
+    most = ctypes.c_int32(0)
+    st = load().wt_validate_pixels(ctypes.byref(p), ctypes.c_void_p(s.data_ptr()) if s.numel() else None,
+                                   ctypes.c_void_p(q.data_ptr()) if q.numel() else None, ctypes.byref(most))
+    if st != 0:
+        raise IndexError(load().wt_last_error().decode("utf-8", "replace"))
+    return int(most.value)
 
 
 def count_launches(n):

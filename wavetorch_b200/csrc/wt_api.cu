@@ -2,8 +2,12 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "wt_common.cuh"
 #include "wt_resident.h"
+#include "wt_slab.h"
 #include "wt_stream.h"
 #include "wt_tile.h"
 
@@ -92,10 +96,44 @@ int wt_query_plan(const wt_problem* p, wt_plan* plan) {
   return make_plan(p, true, false, plan);
 }
 
-int wt_forward(const wt_problem* p, const float* c, const float* b, const float* rho, const float* x,
-               const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, float* u1, float* u2,
-               float* probe_out, float* probe_raw, float* fields_out, void* history, size_t history_bytes,
-               void* workspace, size_t workspace_bytes, void* stream) {
+int wt_validate_pixels(const wt_problem* p, const int32_t* src_ij_host, const int32_t* prb_ij_host, int32_t* max_listings) {
+  WT_TRY(check_problem(p));
+  WT_REQUIRE(p->n_src == 0 || src_ij_host, "wt_validate_pixels: src_ij_host is NULL");
+  WT_REQUIRE(p->n_prb == 0 || prb_ij_host, "wt_validate_pixels: prb_ij_host is NULL");
+  for (int k = 0; k < p->n_src; ++k)
+    WT_REQUIRE(src_ij_host[2 * k] >= 0 && src_ij_host[2 * k] < p->Nx && src_ij_host[2 * k + 1] >= 0 && src_ij_host[2 * k + 1] < p->Ny,
+               "source pixel %d = (%d, %d) lies outside the %dx%d grid", k, src_ij_host[2 * k], src_ij_host[2 * k + 1], p->Nx, p->Ny);
+  for (int k = 0; k < p->n_prb; ++k)
+    WT_REQUIRE(prb_ij_host[2 * k] >= 0 && prb_ij_host[2 * k] < p->Nx && prb_ij_host[2 * k + 1] >= 0 && prb_ij_host[2 * k + 1] < p->Ny,
+               "probe pixel %d = (%d, %d) lies outside the %dx%d grid", k, prb_ij_host[2 * k], prb_ij_host[2 * k + 1], p->Nx, p->Ny);
+  if (max_listings) {
+    std::vector<long long> cells((size_t)p->n_src);
+    for (int k = 0; k < p->n_src; ++k) cells[k] = (long long)src_ij_host[2 * k] * p->Ny + src_ij_host[2 * k + 1];
+    std::sort(cells.begin(), cells.end());
+    int best = 0, run = 0;
+    for (int k = 0; k < p->n_src; ++k) {
+      run = (k > 0 && cells[k] == cells[k - 1]) ? run + 1 : 1;
+      if (run > best) best = run;
+    }
+    *max_listings = best;
+  }
+  return WT_OK;
+}
+
+// wt_forward / wt_slab_forward (slab != NULL: streaming kernels on this rank's slab + in-stream ghost-row exchanges)
+static int forward_impl(const wt_problem* p_in, const wt_slab* slab, const float* c, const float* b, const float* rho,
+                        const float* x, const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, float* u1,
+                        float* u2, float* probe_out, float* probe_raw, float* fields_out, void* history,
+                        size_t history_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+  wt_problem pl;
+  const wt_problem* p = p_in;
+  if (slab) {
+    WT_REQUIRE(p_in != nullptr, "wt_problem is NULL");
+    pl = *p_in;
+    pl.flags |= WT_F_FORCE_STREAM;
+    p = &pl;
+    WT_TRY(slab_check(slab, p->B, p->Nx, p->Ny));
+  }
   wt_plan plan;
   WT_TRY(make_plan(p, true, false, &plan));
   WT_REQUIRE(c && b && x && u1 && u2, "wt_forward: c, b, x, u1, u2 must not be NULL");
@@ -121,14 +159,52 @@ int wt_forward(const wt_problem* p, const float* c, const float* b, const float*
     return resident_forward(p, plan, c, b, rho, x, src_ij, prb_ij, prb_square, u1, u2, probe_out, probe_raw, fields_out,
                             history, workspace, st);
   return stream_forward(p, c, b, rho, x, src_ij, prb_ij, prb_square, u1, u2, probe_out, probe_raw, fields_out, history,
-                        workspace, st);
+                        workspace, st, slab);
 }
 
-int wt_backward(const wt_problem* p, const float* c, const float* b, const float* rho, const int32_t* src_ij,
-                const int32_t* prb_ij, const int32_t* prb_square, const float* grad_probe, const float* probe_raw,
-                const float* grad_fields, const void* history, size_t history_bytes, float* adj1, float* adj2,
-                float* grad_c, float* grad_b, float* grad_rho, float* grad_x, void* workspace, size_t workspace_bytes,
-                void* stream) {
+int wt_forward(const wt_problem* p, const float* c, const float* b, const float* rho, const float* x,
+               const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, float* u1, float* u2,
+               float* probe_out, float* probe_raw, float* fields_out, void* history, size_t history_bytes,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(p, nullptr, c, b, rho, x, src_ij, prb_ij, prb_square, u1, u2, probe_out, probe_raw, fields_out,
+                      history, history_bytes, workspace, workspace_bytes, stream);
+}
+
+int wt_slab_forward(const wt_problem* p, const wt_slab* slab, const float* c, const float* b, const float* rho,
+                    const float* x, const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, float* u1,
+                    float* u2, float* probe_out, float* probe_raw, void* history, size_t history_bytes, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  WT_REQUIRE(slab != nullptr, "wt_slab_forward: slab is NULL");
+  return forward_impl(p, slab, c, b, rho, x, src_ij, prb_ij, prb_square, u1, u2, probe_out, probe_raw, nullptr, history,
+                      history_bytes, workspace, workspace_bytes, stream);
+}
+
+int wt_slab_exchange(const wt_slab* slab, int B, int Nx, int Ny, float* f1, float* f2, int device, void* stream) {
+  WT_REQUIRE(slab && f1 && f2 && B >= 1 && Nx >= 1 && Ny >= 1, "wt_slab_exchange: bad argument");
+  WT_TRY(slab_check(slab, B, Nx, Ny));
+  WT_CUDA(cudaSetDevice(device));
+  return slab_exchange(slab, B, Nx, Ny, f1, f2, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int backward_impl(const wt_problem* p_in, const wt_slab* slab, const float* c, const float* b, const float* rho,
+                         const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, const float* grad_probe,
+                         const float* probe_raw, const float* grad_fields, const void* history, size_t history_bytes,
+                         float* adj1, float* adj2, float* grad_c, float* grad_b, float* grad_rho, float* grad_x,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  wt_problem pl;
+  const wt_problem* p = p_in;
+  if (slab) {
+    WT_REQUIRE(p_in != nullptr, "wt_problem is NULL");
+    pl = *p_in;
+    pl.flags |= WT_F_FORCE_STREAM;
+    p = &pl;
+    WT_TRY(slab_check(slab, p->B, p->Nx, p->Ny));
+    WT_REQUIRE(adj1 && adj2, "wt_slab_backward: adj1/adj2 are required (they are what the neighbours exchange)");
+    if (nonlinear_mask(p) || (p->flags & WT_F_NEED_GRAD_B)) {
+      set_error("wt_slab_backward: saturable damping / Kerr terms / grad_b are not supported under domain decomposition");
+      return WT_EUNSUPPORTED;
+    }
+  }
   wt_plan plan;
   WT_TRY(make_plan(p, true, false, &plan));
   WT_REQUIRE(c && b && history && grad_c, "wt_backward: c, b, history, grad_c must not be NULL");
@@ -162,7 +238,25 @@ int wt_backward(const wt_problem* p, const float* c, const float* b, const float
     return resident_backward(p, plan, c, b, rho, src_ij, prb_ij, prb_square, grad_probe, probe_raw, history, grad_c, grad_b,
                              grad_rho, grad_x, workspace, st);
   return stream_backward(p, c, b, rho, src_ij, prb_ij, prb_square, grad_probe, probe_raw, grad_fields, history, adj1,
-                         adj2, grad_c, grad_b, grad_rho, grad_x, workspace, st);
+                         adj2, grad_c, grad_b, grad_rho, grad_x, workspace, st, slab);
+}
+
+int wt_backward(const wt_problem* p, const float* c, const float* b, const float* rho, const int32_t* src_ij,
+                const int32_t* prb_ij, const int32_t* prb_square, const float* grad_probe, const float* probe_raw,
+                const float* grad_fields, const void* history, size_t history_bytes, float* adj1, float* adj2,
+                float* grad_c, float* grad_b, float* grad_rho, float* grad_x, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  return backward_impl(p, nullptr, c, b, rho, src_ij, prb_ij, prb_square, grad_probe, probe_raw, grad_fields, history,
+                       history_bytes, adj1, adj2, grad_c, grad_b, grad_rho, grad_x, workspace, workspace_bytes, stream);
+}
+
+int wt_slab_backward(const wt_problem* p, const wt_slab* slab, const float* c, const float* b, const float* rho,
+                     const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, const float* grad_probe,
+                     const float* probe_raw, const void* history, size_t history_bytes, float* adj1, float* adj2,
+                     float* grad_c, float* grad_x, void* workspace, size_t workspace_bytes, void* stream) {
+  WT_REQUIRE(slab != nullptr, "wt_slab_backward: slab is NULL");
+  return backward_impl(p, slab, c, b, rho, src_ij, prb_ij, prb_square, grad_probe, probe_raw, nullptr, history, history_bytes,
+                       adj1, adj2, grad_c, nullptr, nullptr, grad_x, workspace, workspace_bytes, stream);
 }
 
 int wt_step_forward(const wt_problem* p, const float* b, int b_batched, const float* c, int c_batched,

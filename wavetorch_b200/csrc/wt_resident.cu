@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   const int tid = L.tid, NT = NTC ? NTC : blockDim.x;
   float k1[R][4], k3[R][4];
   load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
-  unsigned m1, m2;
-  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
+  unsigned m1, m2, m3;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2, m3);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * pitch + 4 + pj : -1;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         if (m1) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t]
-          patch_inject<R>(pr, m1, m2, 0u, xs[t & (2 * TB - 1)]);
+          patch_inject<R>(pr, m1, m2, m3, xs[t & (2 * TB - 1)]);
         }
         L.publish(pitch, fld, PAR ^ 1, pr);
         if (TAPE) {
@@ -202,30 +202,34 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 // sources.  So this kernel is the forward kernel plus the tape: sum_t L(u_{t-1})*P_t accumulates per cell and
 // dLoss/dc = gscale * sum / a3 = (2/c) * sum  (cell.py:36).  dLoss/dx[b,t] = sum over source pixels of P_t/a3.
 // GRADX = 0: dLoss/dx is not wanted, its code is compiled out (shape-specialised instances only); 1: decided at run time.
-template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1>
+// RINGC: tape prefetch depth as a compile-time constant (0 = a.ring, a power of two chosen by resident_plan: small patches
+// run a step in a few hundred nanoseconds and need a deeper ring to cover the HBM latency of the bulk copies).
+template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1, int RINGC = 0>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   const int NT = NTC ? NTC : blockDim.x;
+  const int RG = RINGC ? RINGC : a.ring;
+  const int RG_LOG = RINGC ? (RINGC == 2 ? 1 : RINGC == 4 ? 2 : RINGC == 8 ? 3 : 4) : (31 - __clz(a.ring));
   const int pitch = PITCH ? PITCH : a.pitch;
   const int slab_f = (a.Hc + 2) * pitch;
   const unsigned stage_bytes = (unsigned)(R * NT * sizeof(float4));
 
   extern __shared__ float4 smem4[];
-  float4* ring = smem4;                                        // [RING][R*NT] tape stages
-  float* fld = reinterpret_cast<float*>(ring + RING * R * NT);  // [2][slab]   P
+  float4* ring = smem4;                                        // [RG][R*NT] tape stages
+  float* fld = reinterpret_cast<float*>(ring + RG * R * NT);    // [2][slab]   P
   float* ss = fld + 2 * slab_f;                                 // [2][TB][n_prb] probe seeds
   float* gxs = ss + 2 * TB * a.n_prb;                           // [2][TB]     dLoss/dx staging
   int* pown = reinterpret_cast<int*>(gxs + 2 * TB);             // [n_prb] owning thread, or -1
   int* pcell = pown + a.n_prb;                                  // [n_prb] cell index inside the owner's patch
-  uint64_t* full = reinterpret_cast<uint64_t*>(pcell + a.n_prb);  // [RING]; 8-byte aligned (even word count before)
-  uint64_t* bars = full + RING;                                 // [4] ghost rows
+  uint64_t* full = reinterpret_cast<uint64_t*>(pcell + a.n_prb);  // [MAX_RING]; 8-byte aligned (even word count before)
+  uint64_t* bars = full + MAX_RING;                             // [4] ghost rows
 
   Lane<R> L;
   L.init(a, fld, bars);
   const int tid = L.tid;
   float k1[R][4], k3[R][4];
   load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
-  unsigned m1, m2;
-  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
+  unsigned m1, m2, m3;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2, m3);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     bool mine = li >= 0 && li < a.Hc;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   for (int i = tid; i < 2 * TB; i += NT) gxs[i] = 0.f;
   if (tid == 0) {
-    for (int s = 0; s < RING; ++s) mbar_init(full + s, 1);
+    for (int s = 0; s < RG; ++s) mbar_init(full + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
@@ -292,8 +296,8 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       }
     };
     if (tid == 0) {   // prime the tape ring
-      for (int s = 0; s < RING && s < a.T; ++s) {
-        unsigned slot = (it_global + s) % RING;
+      for (int s = 0; s < RG && s < a.T; ++s) {
+        unsigned slot = (it_global + s) & (RG - 1);
         mbar_expect_tx(full + slot, stage_bytes);
         bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(a.T - 1 - s) * tape_step, stage_bytes, full + slot);
       }
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       constexpr int PAR = decltype(par)::value;
       const float* cur = PAR ? rd1 : rd0;
       const unsigned gi = it_global + it;
-      const unsigned slot = gi & (RING - 1), parity = (gi / RING) & 1u;
+      const unsigned slot = gi & (RG - 1), parity = (gi >> RG_LOG) & 1u;
       L.acquire_ghosts();
       if (L.active) {
         if (GRADX && a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
@@ -339,9 +343,10 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (bit == r * 4 + k) { cv = cu[r][k]; kv = k3[r][k]; }
-            const float q = cv / kv;
+            const float q = kv != 0.f ? cv / kv : 0.f;   // a cell with c == 0 carries no P
             s += q;
             if (m2 >> bit & 1u) s += q;
+            if (m3 >> bit & 1u) s += q;
           }
           atomicAdd(gxs + (t & (2 * TB - 1)), s);
         }
@@ -368,9 +373,9 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       }
       if (t > 0) ++L.npub;
       __syncthreads();
-      if (tid == refill_tid && it + RING < a.T) {   // every thread has read this slot: refill it RING steps ahead
+      if (tid == refill_tid && it + RG < a.T) {   // every thread has read this slot: refill it RG steps ahead
         mbar_expect_tx(full + slot, stage_bytes);
-        bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(t - RING) * tape_step, stage_bytes, full + slot);
+        bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(t - RG) * tape_step, stage_bytes, full + slot);
       }
     };
     using P0 = std::integral_constant<int, 0>;
@@ -412,7 +417,8 @@ __global__ void k_finish_grad_p(const float* __restrict__ G, const float* __rest
   if (i >= plane) return;
   float s = 0.f;
   for (int k = 0; k < n_part; ++k) s += G[(size_t)k * stride + i];
-  grad_c[i] = 2.f * s / c[i];
+  const float ci = c[i];
+  grad_c[i] = ci != 0.f ? 2.f * s / ci : 0.f;   // cell.py:36 is proportional to c: exactly zero where c == 0
 }
 
 // =================================================================================================
@@ -423,9 +429,9 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static size_t smem_fwd_bytes(int Hc, int pitch, int n_prb) {
   return (size_t)2 * (Hc + 2) * pitch * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)(n_prb + 1) * 4 + 4 * 8 + 16;
 }
-static size_t smem_adj_bytes(int Hc, int pitch, int n_prb, int R, int threads) {
-  return (size_t)RING * R * threads * 16 + (size_t)2 * (Hc + 2) * pitch * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
-         (size_t)2 * n_prb * 4 + 8 + RING * 8 + 4 * 8 + 16;
+static size_t smem_adj_bytes(int Hc, int pitch, int n_prb, int R, int threads, int ring) {
+  return (size_t)ring * R * threads * 16 + (size_t)2 * (Hc + 2) * pitch * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
+         (size_t)2 * n_prb * 4 + 8 + MAX_RING * 8 + 4 * 8 + 16;
 }
 
 static int max_threads_for(int R) {
@@ -510,6 +516,14 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
       if ((int)res_nl_smem_adj(Hc, pitch, p->n_prb, R, threads, ring) <= smem_cap) return ring;
     return 0;
   };
+  // linear adjoint: deepest power-of-two ring (<= MAX_RING stages, <= 128 KB) that fits next to the slab buffers.  Big patches
+  // (config 3: 30 KB per stage) get 4 stages as before; small ones (R = 1..2, latency-bound small batches) get 8..16
+  auto ring_lin = [&](int Hc, int R, int threads) {
+    for (int ring = MAX_RING; ring >= 2; ring /= 2)
+      if ((size_t)ring * R * threads * 16 <= (size_t)128 * 1024 &&
+          (int)smem_adj_bytes(Hc, pitch, p->n_prb, R, threads, ring) <= smem_cap) return ring;
+    return 0;
+  };
   int bestC = 0, bestR = 0;
   double best_score = -1;
   for (int C : Cs) {
@@ -522,11 +536,11 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
       if ((C - 1) * Hc >= p->Nx) continue;            // every CTA must own at least one real row
       const int runs = Hc / R, nact = runs * P4, threads = round_up(nact, 32);
       if (threads > (nl ? res_nl_max_threads_rt(R) : max_threads_for(R))) continue;
+      if (threads < p->n_prb) continue;                // the forward kernels sample the probes with one lane per probe
       if (nl) {
         if (!ring_for(Hc, R, threads)) continue;
       } else {
-        size_t sm = need_adjoint ? smem_adj_bytes(Hc, pitch, p->n_prb, R, threads) : smem_fwd_bytes(Hc, pitch, p->n_prb);
-        if ((int)sm > smem_cap) continue;
+        if (need_adjoint ? !ring_lin(Hc, R, threads) : (int)smem_fwd_bytes(Hc, pitch, p->n_prb) > smem_cap) continue;
       }
       // estimated time per step ~ (waves of clusters) x (rows per CTA) / (per-thread efficiency)
       size_t sf, sb;
@@ -537,7 +551,7 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
         ncl = res_nl_clusters_cached(p->device, R, nl, C, threads, sf, sb);
       } else {
         sf = smem_fwd_bytes(Hc, pitch, p->n_prb);
-        sb = smem_adj_bytes(Hc, pitch, p->n_prb, R, threads);
+        sb = smem_adj_bytes(Hc, pitch, p->n_prb, R, threads, ring_lin(Hc, R, threads));
         ncl = resident_clusters(p->device, R, C, threads, sf, sb);
       }
       if (ncl < 1) continue;
@@ -572,9 +586,10 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
     plan->smem_bwd = (int)res_nl_smem_adj(Hc, pitch, p->n_prb, bestR, threads, ring);
     ncl = res_nl_clusters_cached(p->device, bestR, nl, bestC, threads, plan->smem_fwd, plan->smem_bwd);
   } else {
-    plan->reserved[0] = RING;
+    const int ring = ring_lin(Hc, bestR, threads);
+    plan->reserved[0] = ring;
     plan->smem_fwd = (int)smem_fwd_bytes(Hc, pitch, p->n_prb);
-    plan->smem_bwd = (int)smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads);
+    plan->smem_bwd = (int)smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads, ring);
     ncl = resident_clusters(p->device, bestR, bestC, threads, plan->smem_fwd, plan->smem_bwd);
   }
   if (ncl < 1) return false;
@@ -650,8 +665,7 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
   a.tape = reinterpret_cast<float4*>(history);
   a.status = status;
   if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st);
-  const char* esp = getenv("WT_RES_NOSPEC");
-  if (!a.fields && plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(esp && esp[0] == '1')) {   // BASELINE config 3
+  if (!a.fields && plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(a.flags & WT_F_NO_SPECIALIZE)) {   // BASELINE config 3
     if (a.tape) WT_TRY(launch_cluster(k_res_fwd<5, true, 104, 384>, plan, plan.smem_fwd, a, st));
     else WT_TRY(launch_cluster(k_res_fwd<5, false, 104, 384>, plan, plan.smem_fwd, a, st));
     return WT_OK;
@@ -698,10 +712,9 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
     WT_CUDA(cudaGetLastError());
     return WT_OK;
   }
-  const char* esp = getenv("WT_RES_NOSPEC");
-  if (plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(esp && esp[0] == '1')) {   // BASELINE config 3
-    if (a.grad_x) WT_TRY(launch_cluster(k_res_adj<5, 104, 384, 1>, plan, plan.smem_bwd, a, st));
-    else WT_TRY(launch_cluster(k_res_adj<5, 104, 384, 0>, plan, plan.smem_bwd, a, st));
+  if (plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && a.ring == 4 && !(a.flags & WT_F_NO_SPECIALIZE)) {   // BASELINE config 3
+    if (a.grad_x) WT_TRY(launch_cluster(k_res_adj<5, 104, 384, 1, 4>, plan, plan.smem_bwd, a, st));
+    else WT_TRY(launch_cluster(k_res_adj<5, 104, 384, 0, 4>, plan, plan.smem_bwd, a, st));
   } else {
     WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st)));
   }

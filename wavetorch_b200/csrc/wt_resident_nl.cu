@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
 #pragma unroll
       for (int k = 0; k < 4; ++k) ce[r][k] = __frcp_rn(ce[r][k]);
   }
-  unsigned m1, m2;
-  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
+  unsigned m1, m2, m3;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2, m3);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * pitch + 4 + pj : -1;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
             }
             pr[r][k] = wt_update(q + q, q * kc2, u, pr[r][k], lap[r][k]);
           }
-        if (m1) patch_inject<R>(pr, m1, m2, 0u, xs[(blk & 1) * TB + tt]);
+        if (m1) patch_inject<R>(pr, m1, m2, m3, xs[(blk & 1) * TB + tt]);
         L.publish(pitch, fld, (t + 1) & 1, pr);
         if (FIELDS && (t + 1) % a.field_every == 0) {
 #pragma unroll
@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
   const int tid = L.tid;
   float ce[R][4], cf[R][4], cl[R][4], cg[R][4];
   load_nl_consts<R>(a, L.active, L.gi0, L.j0, ce, cf, cl, cg);
-  unsigned m1, m2;
-  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
+  unsigned m1, m2, m3;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2, m3);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     bool mine = li >= 0 && li < a.Hc;
@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
             for (int k = 0; k < 4; ++k) {
               if (m1 >> (r * 4 + k) & 1u) sv += lam[r][k];
               if (m2 >> (r * 4 + k) & 1u) sv += lam[r][k];
+              if (m3 >> (r * 4 + k) & 1u) sv += lam[r][k];
             }
           atomicAdd(gxs + (blk & 1) * TB + tt, sv);
         }
@@ -534,8 +535,7 @@ static int nl_launch(K kernel, const wt_plan& plan, size_t smem, const ResArgs& 
 int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
   const int R = plan.rows_per_thread, nl = plan.nonlinear;
   int rc = WT_EINVAL;
-  const char* esp = getenv("WT_RES_NOSPEC");
-  const bool spec = R == 2 && a.pitch == 104 && plan.threads == 480 && !(esp && esp[0] == '1');   // BASELINE config 4
+  const bool spec = R == 2 && a.pitch == 104 && plan.threads == 480 && !(a.flags & WT_F_NO_SPECIALIZE);   // BASELINE config 4
   if (a.fields) {   // output_fields=True: separate instantiation, keeps the field stores out of the common step body
     WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR, true>, plan, plan.smem_fwd, a, st)))
   } else if (spec) {
@@ -552,8 +552,7 @@ int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
 int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
   const int R = plan.rows_per_thread, nl = plan.nonlinear;
   int rc = WT_EINVAL;
-  const char* esp = getenv("WT_RES_NOSPEC");
-  if (R == 2 && a.pitch == 104 && plan.threads == 480 && !(esp && esp[0] == '1')) {   // BASELINE config 4
+  if (R == 2 && a.pitch == 104 && plan.threads == 480 && !(a.flags & WT_F_NO_SPECIALIZE)) {   // BASELINE config 4
     if (a.grad_x) {
       if (nl == 1) rc = nl_launch(k_res_adj_nl<2, true, false, 104, 480, 1>, plan, plan.smem_bwd, a, st);
       if (nl == 2) rc = nl_launch(k_res_adj_nl<2, false, true, 104, 480, 1>, plan, plan.smem_bwd, a, st);

@@ -8,6 +8,7 @@
 // Reference semantics: wavetorch/rnn.py:50-67 (loop body), cell.py:12-17 / 27-44 / 94-102,
 // operators.py:5-11, source.py:15-22, probe.py:14-27.
 #include "wt_common.cuh"
+#include "wt_slab.h"
 #include "wt_stream.h"
 #include "wt_tile.h"
 
@@ -497,7 +498,7 @@ static int make_offsets(const wt_problem* p, const int32_t* src_ij, const int32_
 int stream_forward(const wt_problem* p, const float* c, const float* b, const float* rho, const float* x,
                    const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_sq, float* u1, float* u2,
                    float* probe_out, float* probe_raw, float* fields_out, void* history, void* workspace,
-                   cudaStream_t st) {
+                   cudaStream_t st, const wt_slab* slab) {
   const size_t plane = (size_t)p->Nx * p->Ny, field = plane * p->B;
   const int nl = nonlinear_mask(p);
   const bool general = nl || (p->flags & WT_F_NEED_GRAD_B);
@@ -519,7 +520,7 @@ int stream_forward(const wt_problem* p, const float* c, const float* b, const fl
   if (!fields_out && tile_eligible(p) && vec4_ok(p, {u1, u2, history, workspace})) {
     // large grid: K time steps per HBM round trip (wt_tile.cu)
     float* extra = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + stream_ws_fwd_base(p));
-    return tile_forward(p, a1, a3, x, src_ij, prb_ij, prb_sq, u1, u2, probe_out, probe_raw, tape, extra, st, nullptr);
+    return tile_forward(p, a1, a3, x, src_ij, prb_ij, prb_sq, u1, u2, probe_out, probe_raw, tape, extra, st, nullptr, slab);
   }
   const bool v4 = vec4_ok(p, {u1, u2, history, fields_out, workspace});
   const int vec = v4 ? 4 : 1;
@@ -551,17 +552,21 @@ int stream_forward(const wt_problem* p, const float* c, const float* b, const fl
     k_src_prb<<<p->B, 128, 0, st>>>(cur2, plane, a.fields, a.fields_bstride, x, t, p->T, off.src, p->n_src, off.prb,
                                     prb_sq, p->n_prb, probe_out, probe_raw);
     float* tmp = cur1; cur1 = cur2; cur2 = tmp;
+    // slab decomposition: refresh the ghost rows every halo steps (halo is even: cur1 == u1 here)
+    if (slab && t + 1 < p->T && (t + 1) % slab->halo == 0) WT_TRY(slab_exchange(slab, p->B, p->Nx, p->Ny, cur1, cur2, st));
   }
   WT_CUDA(cudaGetLastError());
   if (cur1 != u1) k_swap<<<592, 256, 0, st>>>(u1, u2, field);   // odd T: put the latest field back into u1
   WT_CUDA(cudaGetLastError());
+  WT_TRY(slab_exchange(slab, p->B, p->Nx, p->Ny, u1, u2, st));
   return WT_OK;
 }
 
 int stream_backward(const wt_problem* p, const float* c, const float* b, const float* rho, const int32_t* src_ij,
                     const int32_t* prb_ij, const int32_t* prb_sq, const float* grad_probe, const float* probe_raw,
                     const float* grad_fields, const void* history, float* adj1, float* adj2, float* grad_c,
-                    float* grad_b, float* grad_rho, float* grad_x, void* workspace, cudaStream_t st) {
+                    float* grad_b, float* grad_rho, float* grad_x, void* workspace, cudaStream_t st,
+                    const wt_slab* slab) {
   const size_t plane = (size_t)p->Nx * p->Ny, field = plane * p->B;
   const int nl = nonlinear_mask(p);
   const bool general = nl || (p->flags & WT_F_NEED_GRAD_B);
@@ -596,7 +601,7 @@ int stream_backward(const wt_problem* p, const float* c, const float* b, const f
       float* spare1 = chained ? w1 : P;
       float* spare2 = chained ? w2 : extra;
       WT_TRY(tile_backward(p, a1, a3, c, src_ij, prb_ij, prb_sq, grad_probe, probe_raw, tape, l1, l2, spare1, spare2, Gc, grad_c,
-                           grad_x, chained, st));
+                           grad_x, chained, st, slab));
       if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
       if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));
       return WT_OK;
@@ -621,6 +626,8 @@ int stream_backward(const wt_problem* p, const float* c, const float* b, const f
       if (v4) k_stream_adj_lin<4><<<grid, block, 0, st>>>(a);
       else k_stream_adj_lin<1><<<grid, block, 0, st>>>(a);
       float* tmp = l1; l1 = l2; l2 = tmp;   // l1 = lambda_{t-1} (unseeded), l2 = lambda_t
+      const int done = p->T - t;
+      if (slab && t > 0 && done % slab->halo == 0) WT_TRY(slab_exchange(slab, p->B, p->Nx, p->Ny, l1, l2, st));
     }
     WT_CUDA(cudaGetLastError());
     k_finish_grad<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(Gc, gs, 1, plane, plane, grad_c);
@@ -630,9 +637,14 @@ int stream_backward(const wt_problem* p, const float* c, const float* b, const f
       // l1 = dLoss/du1_in, l2 = lambda_0 -> weight it to get dLoss/du2_in; then restore the caller's order
       k_scale_carry<<<592, 256, 0, st>>>(l2, a1, plane, field);
       if (l1 != adj1) k_swap<<<592, 256, 0, st>>>(adj1, adj2, field);
+      WT_TRY(slab_exchange(slab, p->B, p->Nx, p->Ny, adj1, adj2, st));
     }
     WT_CUDA(cudaGetLastError());
     return WT_OK;
+  }
+  if (slab) {
+    set_error("wt_slab_backward: saturable damping / Kerr terms / grad_b are not supported under domain decomposition");
+    return WT_EUNSUPPORTED;
   }
 
   // general path

@@ -11,12 +11,13 @@ size_t stream_ws_bwd_bytes(const wt_problem* p);
 int stream_forward(const wt_problem* p, const float* c, const float* b, const float* rho, const float* x,
                    const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_sq, float* u1, float* u2,
                    float* probe_out, float* probe_raw, float* fields_out, void* history, void* workspace,
-                   cudaStream_t st);
+                   cudaStream_t st, const wt_slab* slab = nullptr);
 
 int stream_backward(const wt_problem* p, const float* c, const float* b, const float* rho, const int32_t* src_ij,
                     const int32_t* prb_ij, const int32_t* prb_sq, const float* grad_probe, const float* probe_raw,
                     const float* grad_fields, const void* history, float* adj1, float* adj2, float* grad_c,
-                    float* grad_b, float* grad_rho, float* grad_x, void* workspace, cudaStream_t st);
+                    float* grad_b, float* grad_rho, float* grad_x, void* workspace, cudaStream_t st,
+                    const wt_slab* slab = nullptr);
 
 int step_forward(const wt_problem* p, const float* b, int bb, const float* c, int cb, const float* y1,
                  const float* y2, float* y, cudaStream_t st);

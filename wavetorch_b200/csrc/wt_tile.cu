@@ -13,6 +13,7 @@
 #include <type_traits>
 
 #include "wt_common.cuh"
+#include "wt_slab.h"
 #include "wt_stream.h"
 #include "wt_tile.h"
 
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (bit == r * 4 + k) { cv = cu[r][k]; kv = k3[r][k]; }
-          const float q = cv / kv;
+          const float q = kv != 0.f ? cv / kv : 0.f;   // c == 0: the cell carries no P
           sx += q;
           if (m2 >> bit & 1u) sx += q;
           if (m3 >> bit & 1u) sx += q;
@@ -480,10 +481,11 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
         if (own_row[r]) {
           float4 hi = latest_in_v ? make_float4(v[r][0], v[r][1], v[r][2], v[r][3]) : make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
           float4 lo = latest_in_v ? make_float4(w[r][0], w[r][1], w[r][2], w[r][3]) : make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-          if (aa.out_lambda) {
-            hi.x /= k3[r][0]; hi.y /= k3[r][1]; hi.z /= k3[r][2]; hi.w /= k3[r][3];
-            lo.x = (1.f - k1[r][0]) * lo.x / k3[r][0]; lo.y = (1.f - k1[r][1]) * lo.y / k3[r][1];
-            lo.z = (1.f - k1[r][2]) * lo.z / k3[r][2]; lo.w = (1.f - k1[r][3]) * lo.w / k3[r][3];
+          if (aa.out_lambda) {   // lambda = P / a3 (0 where c == 0: no P is carried there)
+            auto dv = [](float p, float k) { return k != 0.f ? p / k : 0.f; };
+            hi.x = dv(hi.x, k3[r][0]); hi.y = dv(hi.y, k3[r][1]); hi.z = dv(hi.z, k3[r][2]); hi.w = dv(hi.w, k3[r][3]);
+            lo.x = dv((1.f - k1[r][0]) * lo.x, k3[r][0]); lo.y = dv((1.f - k1[r][1]) * lo.y, k3[r][1]);
+            lo.z = dv((1.f - k1[r][2]) * lo.z, k3[r][2]); lo.w = dv((1.f - k1[r][3]) * lo.w, k3[r][3]);
           }
           *reinterpret_cast<float4*>(o1 + r * a.Ny) = hi;
           *reinterpret_cast<float4*>(o2 + r * a.Ny) = lo;
@@ -523,7 +525,7 @@ __global__ void k_seed_last(float* __restrict__ L, size_t plane, int Ny,
 }
 __global__ void k_finish_grad_c(const float* __restrict__ G, const float* __restrict__ c, size_t plane, float* __restrict__ grad_c) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < plane) grad_c[i] = 2.f * G[i] / c[i];
+  if (i < plane) grad_c[i] = c[i] != 0.f ? 2.f * G[i] / c[i] : 0.f;   // cell.py:36 is proportional to c
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -572,8 +574,11 @@ static TileGeom tile_geom(const wt_problem* p, int force_K = 0) {
 
 int tile_forward(const wt_problem* p, const float* a1, const float* a3, const float* x, const int32_t* src_ij,
                  const int32_t* prb_ij, const int32_t* prb_sq, float* u1, float* u2, float* probe_out, float* probe_raw,
-                 float* tape, float* extra_ws, cudaStream_t st, int* launches) {
+                 float* tape, float* extra_ws, cudaStream_t st, int* launches, const wt_slab* slab) {
   const TileGeom g = tile_geom(p);
+  // slab decomposition: ghost rows are refreshed every slab->halo steps; halo is a multiple of 2K, so the current field
+  // pair is the caller's (peer-mapped) u1/u2 whenever an exchange is due
+  WT_REQUIRE(!slab || slab->halo % (2 * g.K) == 0, "wt_slab: halo=%d must be a multiple of %d", slab ? slab->halo : 0, 2 * g.K);
   const size_t field = (size_t)p->B * p->Nx * p->Ny;
   float* A1 = u1;  float* A2 = u2;              // current pair
   float* B1 = extra_ws; float* B2 = extra_ws + field;
@@ -612,12 +617,15 @@ int tile_forward(const wt_problem* p, const float* a1, const float* a3, const fl
     }
     ++n;
     float* s1 = A1; float* s2 = A2; A1 = B1; A2 = B2; B1 = s1; B2 = s2;
+    const int done = t0 + a.steps;
+    if (slab && done < p->T && done % slab->halo == 0) WT_TRY(slab_exchange(slab, p->B, p->Nx, p->Ny, A1, A2, st));
   }
   WT_CUDA(cudaGetLastError());
   if (A1 != u1) {   // odd number of launches: the result sits in the workspace pair
     WT_CUDA(cudaMemcpyAsync(u1, A1, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
     WT_CUDA(cudaMemcpyAsync(u2, A2, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  WT_TRY(slab_exchange(slab, p->B, p->Nx, p->Ny, u1, u2, st));   // closes the call: the next one starts from fresh ghost rows
   if (launches) *launches = n;
   return WT_OK;
 }
@@ -645,8 +653,9 @@ size_t tile_extra_ws_bwd_bytes(const wt_problem* p) {
 int tile_backward(const wt_problem* p, const float* a1, const float* a3, const float* c, const int32_t* src_ij,
                   const int32_t* prb_ij, const int32_t* prb_sq, const float* grad_probe, const float* probe_raw,
                   const float* tape, float* state1, float* state2, float* spare1, float* spare2, float* G, float* grad_c,
-                  float* grad_x, bool chained, cudaStream_t st) {
+                  float* grad_x, bool chained, cudaStream_t st, const wt_slab* slab) {
   const TileGeom g = tile_geom(p, TILE_ADJ_K);
+  WT_REQUIRE(!slab || (chained && slab->halo % (2 * g.K) == 0), "wt_slab: backward needs adj1/adj2 and halo %% %d == 0", 2 * g.K);
   const size_t plane = (size_t)p->Nx * p->Ny, field = plane * p->B;
   if (grad_x) WT_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)p->B * p->T * sizeof(float), st));
   k_seed_last<<<p->B, 64, 0, st>>>(state1, plane, p->Ny, grad_probe, probe_raw, p->T - 1, p->T, prb_ij, prb_sq, p->n_prb);
@@ -683,6 +692,10 @@ int tile_backward(const wt_problem* p, const float* a1, const float* a3, const f
     }
     WT_TRY(rc);
     float* s1 = A1; float* s2 = A2; A1 = B1; A2 = B2; B1 = s1; B2 = s2;
+    // slab decomposition: the adjoint state (P = a3*lambda between launches: a3 depends on the global row only, so both
+    // sides of an edge agree on the scaling) gets the same ghost-row refresh as the forward fields
+    const int done = p->T - 1 - t_hi + a.steps;
+    if (slab && t_hi - g.K >= 0 && done % slab->halo == 0) WT_TRY(slab_exchange(slab, p->B, p->Nx, p->Ny, A1, A2, st));
   }
   WT_CUDA(cudaGetLastError());
   // now A1 = P_{-1}, A2 = P_0
@@ -692,6 +705,7 @@ int tile_backward(const wt_problem* p, const float* a1, const float* a3, const f
       WT_CUDA(cudaMemcpyAsync(state1, A1, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
       WT_CUDA(cudaMemcpyAsync(state2, A2, field * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
+    WT_TRY(slab_exchange(slab, p->B, p->Nx, p->Ny, state1, state2, st));   // dLoss/du1_in, dLoss/du2_in with fresh ghost rows
   }
   WT_CUDA(cudaGetLastError());
   return WT_OK;

@@ -127,7 +127,9 @@ class _CheckpointedLoop(torch.autograd.Function):
         ctx.shape = (Nx, Ny)
         if want_grad:
             ctx.spec, ctx.segs, ctx.chunks, ctx.ckpts = spec, segs, chunks, ckpts
-            ctx.saved = (x32, c32, b32, rho32)
+            # x32/c32/b32/rho32 may alias the caller's tensors: saved through autograd so that an in-place update between
+            # forward and backward trips the version-counter check instead of silently changing the recomputation
+            ctx.save_for_backward(x32, c32, b32, rho32)
             ctx.dtypes = (x.dtype, c.dtype, b.dtype, rho.dtype if rho is not None else None)
         return out.to(x.dtype)
 
@@ -141,7 +143,7 @@ class _CheckpointedLoop(torch.autograd.Function):
         spec, segs, chunks, ckpts = ctx.spec, ctx.segs, ctx.chunks, ctx.ckpts
         if ckpts is None:
             ckpts = {}
-        x32, c32, b32, rho32 = ctx.saved
+        x32, c32, b32, rho32 = ctx.saved_tensors
         dev = c32.device
         B, T = x32.shape
         Nx, Ny = c32.shape
@@ -252,7 +254,9 @@ class _WaveLoop(torch.autograd.Function):
         ctx.shape = (Nx, Ny)
         if want_grad:
             ctx.prob, ctx.plan, ctx.spec = prob, plan, spec
-            ctx.saved = (c32, b32, rho32, probe_raw, hist)
+            # c32/b32/rho32 may alias the caller's tensors (see _CheckpointedLoop); the tape and the raw probe samples
+            # ride along so that autograd frees them with the graph (and keeps them under retain_graph=True)
+            ctx.save_for_backward(c32, b32, rho32, probe_raw, hist)
             ctx.dtypes = (x.dtype, c.dtype, b.dtype, rho.dtype if rho is not None else None)
         result = fields if spec.output_fields else probe_out
         return result.to(out_dtype)
@@ -265,7 +269,7 @@ class _WaveLoop(torch.autograd.Function):
             return None, None, None, zero, None
         lib = _lib.load()
         prob, plan, spec = ctx.prob, ctx.plan, ctx.spec
-        c32, b32, rho32, probe_raw, hist = ctx.saved
+        c32, b32, rho32, probe_raw, hist = ctx.saved_tensors
         dev = c32.device
         B, T, Nx, Ny = prob.B, prob.T, prob.Nx, prob.Ny
         need = ctx.needs_input_grad
@@ -287,7 +291,6 @@ class _WaveLoop(torch.autograd.Function):
                                  _lib.ptr(grad_x), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(st, "wt_backward")
         _lib.count_launches(plan.launches_bwd)
-        ctx.saved = None
         xd, cd, bd, rd = ctx.dtypes
         if need[3] and grad_rho is None:
             grad_rho = torch.zeros((Nx, Ny), device=dev, dtype=torch.float32)   # linear: rho does not enter the loop
@@ -298,7 +301,11 @@ class _WaveLoop(torch.autograd.Function):
 def wave_rnn(x, c, b, rho, spec):
     """Run the fused time loop.  x [B,T]; c, b, rho [Nx,Ny]; returns [B,T,n_prb] (or [B,T,Nx,Ny])."""
     spec.track_grad = torch.is_grad_enabled()
-    if spec.checkpoint_every and spec.checkpoint_every > 0 and spec.checkpoint_every < x.shape[1]:
+    T = x.shape[1]
+    chunked = bool(spec.batch_chunk) and 0 < spec.batch_chunk < x.shape[0]
+    if (spec.checkpoint_every and 0 < spec.checkpoint_every < T) or (chunked and T > 0 and not spec.output_fields):
+        if not spec.checkpoint_every or spec.checkpoint_every >= T:
+            spec.checkpoint_every = T      # batch chunks without time checkpoints: one segment per chunk
         return _CheckpointedLoop.apply(x, c, b, rho, spec)
     return _WaveLoop.apply(x, c, b, rho, spec)
 

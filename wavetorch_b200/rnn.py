@@ -48,11 +48,8 @@ class WaveRNN(torch.nn.Module):
         prb_ij, prb_counts = gather(self.probes)
         prb_sq = torch.tensor([int(getattr(p, "squared", False)) for p, n in zip(self.probes, prb_counts)
                                for _ in range(n)], dtype=torch.int32)
-        # the on-chip kernels handle a pixel listed at most twice (rnn.py:56-57 adds x once per listing)
-        many = False
-        if src_ij.shape[0]:
-            flat = src_ij[:, 0].to(torch.int64) * Ny + src_ij[:, 1]
-            many = bool(torch.bincount(flat).max() > 2)
+        # the on-chip kernels add x at most WT_MAX_SRC_LISTINGS times per pixel (rnn.py:56-57 adds it once per listing)
+        many = _lib.validate_pixels(Nx, Ny, src_ij, prb_ij) > _lib.WT_MAX_SRC_LISTINGS
         tables = dict(src_ij=src_ij.contiguous().to(device), prb_ij=prb_ij.contiguous().to(device),
                       prb_sq=prb_sq.to(device), prb_counts=prb_counts, force_stream=many,
                       scalar_probes=all(p.x.dim() == 0 for p in self.probes))
