@@ -271,7 +271,8 @@ def test_full_size_properties():
     assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g1.cpu().numpy()) < 2e-5
 
 
-@pytest.mark.parametrize("cluster,rows", [(2, 5), (2, 3), (2, 4), (4, 2), (4, 4), (4, 5), (8, 1), (8, 2), (8, 5)])
+@pytest.mark.parametrize("cluster,rows", [(2, 5), (2, 3), (2, 4), (4, 2), (4, 4), (4, 5), (8, 1), (8, 2), (8, 5),
+                                          (3, 5), (5, 2), (6, 3), (7, 2), (10, 1), (12, 1), (15, 1)])
 def test_resident_decompositions_agree(cluster, rows):
     """Every (cluster size, rows per thread) decomposition of the on-chip path computes the same thing."""
     B, T = 5, 130
@@ -964,3 +965,37 @@ def test_deep_tape_ring_small_batches():
     m.plan_flags = _lib.WT_F_FORCE_STREAM
     _loss_head(m(x), lab).backward()
     assert rel_l2(g1.cpu().numpy(), m.cell.geom.rho.grad.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("want_xgrad", [False, True])
+@pytest.mark.parametrize("case", ["vowel_b6", "linear_yml_b9", "lens_b1"])
+def test_shape_specialisation_table(case, want_xgrad, monkeypatch):
+    """The table of shape-specialised instantiations (csrc/wt_resident.cu: WT_SPEC_SHAPES) covers the plans of the
+    reference's study configs at THEIR batch sizes -- example.yml 150x100 at batch 6, linear.yml 140x140 at batch 9,
+    propagate / optimize_lens 151x151 at batch 1 -- and each entry is bit-for-bit the generic kernel."""
+    if case == "vowel_b6":
+        build, (Nx, Ny, B, T), expect = _vowel_model, (150, 100, 6, 150), (2, 104, 256, 16)
+    elif case == "linear_yml_b9":
+        build, (Nx, Ny, B, T), expect = (lambda: _vowel_model(Nx=140, Ny=140)), (140, 140, 9, 150), (2, 144, 320, 8)
+    else:
+        build, (Nx, Ny, B, T), expect = (lambda: _lens_model(0.5)), (151, 151, 1, 150), (2, 156, 384, 8)
+    n_src = 51 if case == "lens_b1" else 1
+    plan = _lib.query_plan(_lib.make_problem(Nx, Ny, B, T, n_src, 3, 1.0, 1.0, flags=_lib.WT_F_ZERO_INIT))
+    assert plan.path == _lib.WT_PATH_RESIDENT
+    assert (plan.rows_per_thread, 4 * ((Ny + 3) // 4) + 4, plan.threads, plan.reserved[0]) == expect
+    x0 = wo.synthetic_vowels(B, T)
+    w = torch.tensor(np.random.RandomState(7).rand(B, T, 3), dtype=torch.float32, device=DEV)
+    res = []
+    for nospec in ("1", "0"):
+        monkeypatch.setenv("WT_RES_NOSPEC", nospec)
+        m = build()
+        x = torch.tensor(x0, device=DEV, requires_grad=want_xgrad)
+        out = m(x)
+        (out * w).sum().backward()
+        res.append((out.detach().clone(), m.cell.geom.rho.grad.clone(), x.grad.clone() if want_xgrad else None))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
+    if want_xgrad and case != "lens_b1":
+        assert torch.equal(res[0][2], res[1][2])
+    elif want_xgrad:   # 51 source pixels spread over 13 threads: their shared-memory atomics add in any order
+        assert rel_l2(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 1e-6

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 // run a step in a few hundred nanoseconds and need a deeper ring to cover the HBM latency of the bulk copies).
 template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1, int RINGC = 0>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
+  constexpr bool EARLY = R <= 2;   // see the step body
   const int NT = NTC ? NTC : blockDim.x;
   const int RG = RINGC ? RINGC : a.ring;
   const int RG_LOG = RINGC ? (RINGC == 2 ? 1 : RINGC == 4 ? 2 : RINGC == 8 ? 3 : 4) : (31 - __clz(a.ring));
@@ -330,6 +331,24 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       const unsigned gi = it_global + it;
       const unsigned slot = gi & (RG - 1), parity = (gi >> RG_LOG) & 1u;
       L.acquire_ghosts();
+      // EARLY (small patches): the stencil update and the ghost-row push come first, the tape stage and the gradient
+      // accumulation -- which need neither the ghost rows nor the new field -- after.  With a handful of rows per CTA the
+      // step time is the ring  push -> DSMEM flight -> neighbour's wait -> its update -> its push;  everything an edge
+      // warp does between its wait and its push sits on that ring.  Big patches (config 3: R = 5) keep the old order:
+      // there the step is issue-bound and consuming the tape stage first frees its registers before the stencil.
+      auto stencil = [&]() {
+        if (t > 0) {
+          float lap[R][4];
+          patch_laplacian<R>(pitch, cur, cu, lap);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
+          add_seeds(pr, t - 1);
+          L.publish(pitch, fld, PAR ^ 1, pr);
+        }
+      };
+      if (EARLY && L.active) stencil();
       if (L.active) {
         if (GRADX && a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
           // a loop over the (few) source cells of this thread with one division each: 4R unrolled divisions would
@@ -360,16 +379,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
           G[r][2] = fmaf(l.z, cu[r][2], G[r][2]);
           G[r][3] = fmaf(l.w, cu[r][3], G[r][3]);
         }
-        if (t > 0) {
-          float lap[R][4];
-          patch_laplacian<R>(pitch, cur, cu, lap);
-#pragma unroll
-          for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
-          add_seeds(pr, t - 1);
-          L.publish(pitch, fld, PAR ^ 1, pr);
-        }
+        if (!EARLY) stencil();
       }
       if (t > 0) ++L.npub;
       __syncthreads();
@@ -436,8 +446,8 @@ static size_t smem_adj_bytes(int Hc, int pitch, int n_prb, int R, int threads, i
 
 static int max_threads_for(int R) {
   switch (R) {
-    case 1: return 1024;
-    case 2: return 768;
+    case 1: return 512;
+    case 2: return 512;
     case 3: return 640;
     case 4: return 512;
     case 5: return 384;
@@ -508,7 +518,7 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
   const int smem_cap = (int)prop.sharedMemPerBlockOptin;
   static const int Rs_lin[] = {8, 6, 5, 4, 3, 2, 1};
   static const int Rs_nl[] = {4, 3, 2, 1};
-  static const int Cs[] = {1, 2, 4, 8, 16};
+  static const int Cs[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 16};   // any cluster size works; > 8 is non-portable (opt-in)
   const int* Rs = nl ? Rs_nl : Rs_lin;
   const int nR = nl ? 4 : 7;
   auto ring_for = [&](int Hc, int R, int threads) {   // deepest tape ring that fits (nonlinear stages are twice as big)
@@ -564,7 +574,18 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
       const double par = threads >= 384 ? 1.0 : threads / 384.0;
       // measured: linear R = 4..5 beats 6..8; the nonlinear adjoint keeps ~10 values per cell live and is fastest at R = 1
       const double regs = nl ? (R == 1 ? 1.6 : R == 2 ? 1.0 : 0.6) : (R >= 6 ? 0.8 : 1.0);
-      const double score = (rim * lane * sync_cost * par * regs) / ((double)waves * Hc * per_sm);
+      double score = (rim * lane * sync_cost * par * regs) / ((double)waves * Hc * per_sm);
+      if (!nl) {
+        // Linear kernels: a cost model fitted to measured sweeps (profiles/r2_sweeps.md; fwd-with-tape + adjoint, us per time
+        // step of one CTA with Hc rows of 100 cells):  t = a_R + b_R * Hc.  The fixed part a_R is the latency chain of one
+        // thread's patch plus the step barrier (small patches win when there are SMs to spread over), the slope b_R the
+        // issue-bound rate (big patches win when every SM is busy).  score = 1 / (waves * t).
+        static const double aR[9] = {0, 0.57, 0.65, 1.70, 0.98, 1.30, 1.30, 0, 1.275};
+        static const double bR[9] = {0, 0.031, 0.0185, 0.004, 0.017, 0.0092, 0.0098, 0, 0.0104};
+        const double t = aR[R] + bR[R] * Hc * (P4 / 25.0) * (per_sm > 1 ? per_sm : 1);
+        score = 1.0 / ((double)waves * t);
+        score *= 1.0 - 1e-3 * C;      // ties: the smaller cluster
+      }
       if (score > best_score) { best_score = score; bestC = C; bestR = R; }
     }
   }
@@ -630,6 +651,17 @@ static int launch_cluster(K kernel, const wt_plan& plan, size_t smem, const ResA
   return WT_OK;
 }
 
+// Shape-specialised instantiations: (rows per thread, row pitch, threads per CTA, tape ring) as compile-time constants, so
+// that every shared-memory and tape offset of the step body is an immediate (5-14 % on the step).  One entry per plan the
+// planner picks for the grids and batch sizes of the reference's study configs; anything else runs the generic kernels
+// (bitwise the same results: tests/test_gpu_parity.py::test_shape_specialised_kernels_match_generic_ones).
+//   X(R, PITCH, THREADS, RING)
+#define WT_SPEC_SHAPES(X)                                                                                              \
+  X(5, 104, 384, 4)  /* 150x100, C=2: study/example.yml geometry at B >= 64 (BASELINE config 3, bench.py)          */ \
+  X(2, 104, 256, 16) /* 150x100, C=8: example.yml at its own batch_size 6; config 3 sharded 8 per GPU             */ \
+  X(2, 144, 320, 8)  /* 140x140, C=8: study/linear/linear.yml (batch_size 9)                                      */ \
+  X(2, 156, 384, 8)  /* 151x151, C=8: study/propagate.py, study/optimize_lens.py (BASELINE configs 1-2)           */
+
 #define WT_DISPATCH_R(R_, CALL)                  \
   switch (R_) {                                  \
     case 1: { constexpr int R = 1; CALL; } break; \
@@ -665,10 +697,15 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
   a.tape = reinterpret_cast<float4*>(history);
   a.status = status;
   if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st);
-  if (!a.fields && plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && !(a.flags & WT_F_NO_SPECIALIZE)) {   // BASELINE config 3
-    if (a.tape) WT_TRY(launch_cluster(k_res_fwd<5, true, 104, 384>, plan, plan.smem_fwd, a, st));
-    else WT_TRY(launch_cluster(k_res_fwd<5, false, 104, 384>, plan, plan.smem_fwd, a, st));
-    return WT_OK;
+  if (!a.fields && !(a.flags & WT_F_NO_SPECIALIZE)) {
+#define WT_SPEC_F(R_, P_, N_, G_)                                                                       \
+    if (plan.rows_per_thread == R_ && a.pitch == P_ && plan.threads == N_) {                              \
+      if (a.tape) WT_TRY(launch_cluster(k_res_fwd<R_, true, P_, N_>, plan, plan.smem_fwd, a, st));        \
+      else WT_TRY(launch_cluster(k_res_fwd<R_, false, P_, N_>, plan, plan.smem_fwd, a, st));              \
+      return WT_OK;                                                                                       \
+    }
+    WT_SPEC_SHAPES(WT_SPEC_F)
+#undef WT_SPEC_F
   }
   if (a.fields) {
     if (a.tape) { wt::set_error("wt_forward: fields_out together with history needs WT_F_FORCE_STREAM"); return WT_EUNSUPPORTED; }
@@ -712,12 +749,18 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
     WT_CUDA(cudaGetLastError());
     return WT_OK;
   }
-  if (plan.rows_per_thread == 5 && a.pitch == 104 && plan.threads == 384 && a.ring == 4 && !(a.flags & WT_F_NO_SPECIALIZE)) {   // BASELINE config 3
-    if (a.grad_x) WT_TRY(launch_cluster(k_res_adj<5, 104, 384, 1, 4>, plan, plan.smem_bwd, a, st));
-    else WT_TRY(launch_cluster(k_res_adj<5, 104, 384, 0, 4>, plan, plan.smem_bwd, a, st));
-  } else {
-    WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st)));
+  bool launched = false;
+  if (!(a.flags & WT_F_NO_SPECIALIZE)) {
+#define WT_SPEC_A(R_, P_, N_, G_)                                                                               \
+    if (!launched && plan.rows_per_thread == R_ && a.pitch == P_ && plan.threads == N_ && a.ring == G_) {         \
+      if (a.grad_x) WT_TRY(launch_cluster(k_res_adj<R_, P_, N_, 1, G_>, plan, plan.smem_bwd, a, st));             \
+      else WT_TRY(launch_cluster(k_res_adj<R_, P_, N_, 0, G_>, plan, plan.smem_bwd, a, st));                      \
+      launched = true;                                                                                            \
+    }
+    WT_SPEC_SHAPES(WT_SPEC_A)
+#undef WT_SPEC_A
   }
+  if (!launched) { WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R>, plan, plan.smem_bwd, a, st))); }
   k_finish_grad_p<<<fg, 256, 0, st>>>(Gpart, c, plan.n_clusters, plane, plane, grad_c);
   if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
   if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));

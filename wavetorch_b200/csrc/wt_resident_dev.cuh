@@ -242,7 +242,9 @@ __device__ __forceinline__ void patch_laplacian(int pitch, const float* own, con
 
 template <int R>
 constexpr int res_max_threads() {
-  return R <= 1 ? 1024 : R == 2 ? 768 : R == 3 ? 640 : R == 4 ? 512 : R == 5 ? 384 : R == 6 ? 320 : 256;
+  // R <= 2: 512 threads (128 registers) rather than the 1024 / 768 a small patch would allow: at 64 / 85 registers the
+  // adjoint spills inside the time loop, and decompositions that would need more threads pick a larger R anyway
+  return R <= 2 ? 512 : R == 3 ? 640 : R == 4 ? 512 : R == 5 ? 384 : R == 6 ? 320 : 256;
 }
 
 // host entry points of wt_resident_nl.cu
