@@ -112,7 +112,7 @@ int wt_query_plan(const wt_problem* p, wt_plan* plan);
  * must set WT_F_FORCE_STREAM -- the on-chip kernels add x[b,t] at most that many times per pixel (rnn.py:56-57 adds it
  * once per listing; the streaming kernels handle any count).
  */
-#define WT_MAX_SRC_LISTINGS 3
+#define WT_MAX_SRC_LISTINGS 2
 int wt_validate_pixels(const wt_problem* p, const int32_t* src_ij_host, const int32_t* prb_ij_host, int32_t* max_listings);
 
 /*

@@ -127,7 +127,7 @@ def query_plan(problem):
     return plan
 
 
-WT_MAX_SRC_LISTINGS = 3
+WT_MAX_SRC_LISTINGS = 2
 
 
 def validate_pixels(Nx, Ny, src_ij_host, prb_ij_host):

@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   const int tid = L.tid, NT = NTC ? NTC : blockDim.x;
   float k1[R][4], k3[R][4];
   load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
-  unsigned m1, m2, m3;
-  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2, m3);
+  unsigned m1, m2;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * pitch + 4 + pj : -1;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         if (m1) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t]
-          patch_inject<R>(pr, m1, m2, m3, xs[t & (2 * TB - 1)]);
+          patch_inject<R>(pr, m1, m2, 0u, xs[t & (2 * TB - 1)]);
         }
         L.publish(pitch, fld, PAR ^ 1, pr);
         if (TAPE) {
@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   const int tid = L.tid;
   float k1[R][4], k3[R][4];
   load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
-  unsigned m1, m2, m3;
-  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2, m3);
+  unsigned m1, m2;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     bool mine = li >= 0 && li < a.Hc;
@@ -365,7 +365,6 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
             const float q = kv != 0.f ? cv / kv : 0.f;   // a cell with c == 0 carries no P
             s += q;
             if (m2 >> bit & 1u) s += q;
-            if (m3 >> bit & 1u) s += q;
           }
           atomicAdd(gxs + (t & (2 * TB - 1)), s);
         }

@@ -184,20 +184,20 @@ struct Lane {
   }
 };
 
-// Which of my 4R cells are sources?  m1 / m2 / m3: listed at least once / twice / three times (rnn.py:56-57 adds x
-// once per listing).  More than three listings of one pixel are not supported by this path: the status word is set and
-// wt_validate_pixels() tells the caller beforehand (include/wavetorch_b200.h).
+// Which of my 4R cells are sources?  m1 / m2: listed at least once / twice (rnn.py:56-57 adds x once per listing).
+// More than two listings of one pixel are not supported by this path (a third mask in the step body costs the common case
+// 5 % through code size alone): the status word is set and wt_validate_pixels() tells the caller beforehand
+// (include/wavetorch_b200.h: WT_MAX_SRC_LISTINGS); the Python binding routes such models to the streaming kernels.
 template <int R>
 __device__ __forceinline__ void source_masks(const ResArgs& a, bool active, int gi0, int j0, unsigned& m1,
-                                             unsigned& m2, unsigned& m3) {
-  m1 = 0; m2 = 0; m3 = 0;
+                                             unsigned& m2) {
+  m1 = 0; m2 = 0;
   if (!active) return;
   for (int s = 0; s < a.n_src; ++s) {
     int si = a.src_ij[2 * s] - gi0, sj = a.src_ij[2 * s + 1] - j0;
     if (si >= 0 && si < R && sj >= 0 && sj < 4) {
       unsigned bit = 1u << (si * 4 + sj);
-      if (m3 & bit) atomicExch(a.status, 1);
-      else if (m2 & bit) m3 |= bit;
+      if (m2 & bit) atomicExch(a.status, 1);
       else if (m1 & bit) m2 |= bit;
       else m1 |= bit;
     }

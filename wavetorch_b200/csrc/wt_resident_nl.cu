@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
 #pragma unroll
       for (int k = 0; k < 4; ++k) ce[r][k] = __frcp_rn(ce[r][k]);
   }
-  unsigned m1, m2, m3;
-  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2, m3);
+  unsigned m1, m2;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * pitch + 4 + pj : -1;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
             }
             pr[r][k] = wt_update(q + q, q * kc2, u, pr[r][k], lap[r][k]);
           }
-        if (m1) patch_inject<R>(pr, m1, m2, m3, xs[(blk & 1) * TB + tt]);
+        if (m1) patch_inject<R>(pr, m1, m2, 0u, xs[(blk & 1) * TB + tt]);
         L.publish(pitch, fld, (t + 1) & 1, pr);
         if (FIELDS && (t + 1) % a.field_every == 0) {
 #pragma unroll
@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
   const int tid = L.tid;
   float ce[R][4], cf[R][4], cl[R][4], cg[R][4];
   load_nl_consts<R>(a, L.active, L.gi0, L.j0, ce, cf, cl, cg);
-  unsigned m1, m2, m3;
-  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2, m3);
+  unsigned m1, m2;
+  source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     bool mine = li >= 0 && li < a.Hc;
@@ -350,7 +350,6 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
             for (int k = 0; k < 4; ++k) {
               if (m1 >> (r * 4 + k) & 1u) sv += lam[r][k];
               if (m2 >> (r * 4 + k) & 1u) sv += lam[r][k];
-              if (m3 >> (r * 4 + k) & 1u) sv += lam[r][k];
             }
           atomicAdd(gxs + (blk & 1) * TB + tt, sv);
         }
