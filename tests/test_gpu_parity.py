@@ -1002,3 +1002,40 @@ def test_shape_specialisation_table(case, want_xgrad, monkeypatch):
         assert torch.equal(res[0][2], res[1][2])
     elif want_xgrad:   # 51 source pixels spread over 13 threads: their shared-memory atomics add in any order
         assert rel_l2(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("B,T,S,cluster,rows", [(6, 1000, 128, 0, 0), (5, 333, 64, 2, 5), (3, 200, 100, 8, 1), (9, 257, 64, 4, 3)])
+def test_onchip_checkpoint_and_recompute(B, T, S, cluster, rows):
+    """north_star kernel (2): checkpoint-and-recompute of field snapshots on the on-chip path.  model.checkpoint_every = S:
+    the forward writes no tape, only register-patch snapshots every S steps (rounded up to a multiple of 64); the backward
+    re-runs each segment with a one-segment tape and chains the adjoint.  Same probes (bitwise) and gradients (to the
+    order of the per-segment partial sums) as the store-everything run; B = 6, T = 1000 is the reference fixture."""
+    m = _vowel_model()
+    m.cluster, m.rows_per_thread = cluster, rows
+    x0 = wo.synthetic_vowels(B, T)
+    w = torch.tensor(np.random.RandomState(1).rand(B, T, 3), dtype=torch.float32, device=DEV)
+    x = torch.tensor(x0, device=DEV, requires_grad=True)
+    out_ref = m(x)
+    (out_ref * w).sum().backward()
+    g_ref, gx_ref = m.cell.geom.rho.grad.clone(), x.grad.clone()
+    m.zero_grad(); x.grad = None
+    m.checkpoint_every = S
+    p = _lib.make_problem(150, 100, B, T, 1, 3, 1.0, 1.4283556979968262, flags=_lib.WT_F_ZERO_INIT, cluster=cluster, rows_per_thread=rows)
+    full = int(_lib.query_plan(p).history_bytes)
+    p.checkpoint_every = S
+    plan = _lib.query_plan(p)
+    assert plan.path == _lib.WT_PATH_RESIDENT and plan.reserved[2] == (S + 63) // 64 * 64
+    assert int(plan.history_bytes) < full            # that is the point
+    l0 = _lib.launch_count
+    out = m(x)
+    (out * w).sum().backward()
+    assert _lib.launch_count - l0 < 60                # on-chip: a few launches per segment, not one per time step
+    assert torch.equal(out.detach(), out_ref.detach())
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g_ref.cpu().numpy()) < 2e-6
+    assert rel_l2(x.grad.cpu().numpy(), gx_ref.cpu().numpy()) < 2e-6
+    if (B, T) == (6, 1000):
+        g = load_golden("vowel_linear")
+        m.zero_grad()
+        xg = torch.tensor(g["x_f64"], dtype=torch.float32, device=DEV)
+        _loss_head(m(xg), torch.arange(6, device=DEV) % 3).backward()
+        assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f32"]) < 1e-4

@@ -30,7 +30,7 @@ class WtProblem(ctypes.Structure):
                 ("device", ctypes.c_int32), ("dt", ctypes.c_double), ("h", ctypes.c_double),
                 ("b0", ctypes.c_double), ("uth", ctypes.c_double), ("c_nl", ctypes.c_double),
                 ("cluster", ctypes.c_int32), ("rows_per_thread", ctypes.c_int32), ("field_every", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 5)]
+                ("checkpoint_every", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
 
 
 class WtPlan(ctypes.Structure):

@@ -35,7 +35,10 @@ namespace wt {
 // BASELINE config-3 shape is instantiated with constants: every shared-memory and tape offset of the step becomes an immediate.
 // FIELDS: also write every field to HBM (output_fields=True); a separate instantiation keeps that code out of the step body
 // of the common kernels, which is fetched from the instruction cache 2T times per sample.
-template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false>
+// CKPT: the checkpoint-and-recompute instantiation -- the launch covers steps [t_off, t_off + T) of longer sequences, can
+// start from a stored snapshot of the register patches and stores snapshots every snap_every steps (a multiple of TB) on
+// its way; the common kernels carry none of that code.
+template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false, bool CKPT = false>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
   const int pitch = PITCH ? PITCH : a.pitch;
@@ -71,14 +74,25 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         int gi = L.gi0 + r, j = L.j0 + k;
-        bool ok = L.active && gi < a.Nx && j < a.Ny && !(a.flags & WT_F_ZERO_INIT);
+        bool ok = !CKPT && L.active && gi < a.Nx && j < a.Ny && !(a.flags & WT_F_ZERO_INIT);
         size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
         v[r][k] = ok ? a.u1[o] : 0.f;
         w[r][k] = ok ? a.u2[o] : 0.f;
       }
+    if (CKPT && a.snap_in) {   // resume from a snapshot: my own registers, as I stored them
+      const float4* sp = a.snap_in + ((size_t)b * a.C + L.rank) * 2 * R * NT + tid;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 p = sp[r * NT], q = sp[(R + r) * NT];
+        v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
+        w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
+      }
+    }
     if (L.active) L.publish(pitch, fld, 0, v);
     ++L.npub;
-    const float* xb = a.x + (size_t)b * a.T;
+    const int Tst = CKPT ? a.Tstride : a.T;         // length of the sequences x / probe_out are laid out for
+    const int toff = CKPT ? a.t_off : 0;
+    const float* xb = a.x + (size_t)b * Tst + toff;
     for (int i = tid; i < TB && i < a.T; i += NT) xs[i] = xb[i];
     __syncthreads();
 
@@ -92,7 +106,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
         int p = i % a.n_prb;
         if (poff[p] >= 0) {
           float val = src[i];
-          size_t o = ((size_t)b * a.T + t0 + i / a.n_prb) * a.n_prb + p;
+          size_t o = ((size_t)b * Tst + toff + t0 + i / a.n_prb) * a.n_prb + p;
           if (a.probe_raw) a.probe_raw[o] = val;
           if (a.probe_out) a.probe_out[o] = a.prb_sq[p] ? val * val : val;
         }
@@ -157,6 +171,14 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
         for (int i = tid; i < TB && t1 + i < a.T; i += NT) dst[i] = xb[t1 + i];
       }
       if (blk >= 2) flush(blk - 2);
+      if (CKPT && a.snap_every && t0 > 0 && (toff + t0) % a.snap_every == 0) {   // v = u_{t-1}, w = u_{t-2}: blocks are even
+        float4* sp = a.snap + ((((size_t)((toff + t0) / a.snap_every - 1) * a.B + b) * a.C + L.rank) * 2 * R) * NT + tid;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          sp[r * NT] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+          sp[(R + r) * NT] = make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
+        }
+      }
       int tt = 0;
       for (; tt + 1 < n; tt += 2) {     // two steps per iteration: the two time levels swap roles, no moves
         step(P0{}, v, w, t0 + tt);
@@ -180,7 +202,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         int gi = L.gi0 + r, j = L.j0 + k;
-        if (L.active && gi < a.Nx && j < a.Ny) {
+        if (L.active && gi < a.Nx && j < a.Ny && (!CKPT || a.u1)) {
           size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
           a.u1[o] = v[r][k];
           a.u2[o] = w[r][k];
@@ -204,7 +226,10 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 // GRADX = 0: dLoss/dx is not wanted, its code is compiled out (shape-specialised instances only); 1: decided at run time.
 // RINGC: tape prefetch depth as a compile-time constant (0 = a.ring, a power of two chosen by resident_plan: small patches
 // run a step in a few hundred nanoseconds and need a deeper ring to cover the HBM latency of the bulk copies).
-template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1, int RINGC = 0>
+// CHAIN: the checkpoint-and-recompute instantiation -- the launch covers the reverse steps of the segment [t_off, t_off+T)
+// of longer sequences; the pair (P_{t-1}, P_t) at the segment boundary is handed from launch to launch through a.chain
+// in the register layout (no lambda <-> P conversion, no division), and the per-cluster gradient partials accumulate.
+template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1, int RINGC = 0, bool CHAIN = false>
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   constexpr bool EARLY = R <= 2;   // see the step body
   const int NT = NTC ? NTC : blockDim.x;
@@ -264,12 +289,14 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   unsigned it_global = 0;   // tape stages consumed so far (ring slot / parity bookkeeping across samples)
   for (int b = L.cid; b < a.B; b += a.n_clusters) {
     const float4* tape_b = a.tape + (((size_t)b * a.T) * a.C + L.rank) * R * NT;   // stage of step t at + t*tape_step
+    const int Tst = CHAIN ? a.Tstride : a.T;        // length of the sequences grad_probe / probe_raw / grad_x are laid out for
+    const int toff = CHAIN ? a.t_off : 0;
     auto stage_seeds = [&](int blk) {   // seeds of time block blk: dLoss/d(raw probe value)
       const int t0 = blk * TB, n = min(TB, a.T - t0);
       float* dst = ss + (blk & 1) * TB * a.n_prb;
       for (int i = tid; i < n * a.n_prb; i += NT) {
         int p = i % a.n_prb;
-        size_t o = ((size_t)b * a.T + t0 + i / a.n_prb) * a.n_prb + p;
+        size_t o = ((size_t)b * Tst + toff + t0 + i / a.n_prb) * a.n_prb + p;
         float g = a.grad_probe[o];
         if (a.prb_sq[p]) g *= 2.f * a.probe_raw[o];   // probe.py:27
         dst[i] = g;
@@ -281,7 +308,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       for (int i = tid; i < n; i += NT) {
         float s = src[i];
         src[i] = 0.f;
-        if (s != 0.f) atomicAdd(a.grad_x + (size_t)b * a.T + t0 + i, s);
+        if (s != 0.f) atomicAdd(a.grad_x + (size_t)b * Tst + toff + t0 + i, s);
       }
     };
     // P += a3 * seed_t at the probe cells of my patch.  The common case (at most one probe per thread) needs one shared
@@ -313,6 +340,15 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k) { v[r][k] = 0.f; w[r][k] = 0.f; }
+    if (CHAIN && a.chain_in) {   // (P_{T-1} before its seeds, P_T) as the later segment left them
+      const float4* cp = a.chain + ((size_t)b * a.C + L.rank) * 2 * R * NT + tid;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 p = cp[r * NT], q = cp[(R + r) * NT];
+        v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
+        w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
+      }
+    }
     if (L.active) {
       add_seeds(v, a.T - 1);
       L.publish(pitch, fld, 0, v);
@@ -337,15 +373,17 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
       // warp does between its wait and its push sits on that ring.  Big patches (config 3: R = 5) keep the old order:
       // there the step is issue-bound and consuming the tape stage first frees its registers before the stencil.
       auto stencil = [&]() {
-        if (t > 0) {
+        if (t > 0 || (CHAIN && a.chain_out)) {   // chained: P_{-1} of this segment is P_{T-1} of the one before it
           float lap[R][4];
           patch_laplacian<R>(pitch, cur, cu, lap);
 #pragma unroll
           for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
-          add_seeds(pr, t - 1);
-          L.publish(pitch, fld, PAR ^ 1, pr);
+          if (!CHAIN || t > 0) {
+            add_seeds(pr, t - 1);
+            L.publish(pitch, fld, PAR ^ 1, pr);
+          }
         }
       };
       if (EARLY && L.active) stencil();
@@ -405,6 +443,17 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     }
     if (t == 0) step(P0{}, v, w, 0, it);
     it_global += (unsigned)a.T;
+    if (CHAIN && a.chain_out) {   // (P_{-1}, P_0): after an even number of steps they sit in (v, w), else in (w, v)
+      float4* cp = a.chain + ((size_t)b * a.C + L.rank) * 2 * R * NT + tid;
+      const bool even = (a.T & 1) == 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 p = even ? make_float4(v[r][0], v[r][1], v[r][2], v[r][3]) : make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
+        const float4 q = even ? make_float4(w[r][0], w[r][1], w[r][2], w[r][3]) : make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+        cp[r * NT] = p;
+        cp[(R + r) * NT] = q;
+      }
+    }
     __syncthreads();
     if (GRADX && a.grad_x) flush_gx(0);
     __syncthreads();
@@ -415,7 +464,10 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int gi = L.gi0 + r, j = L.j0 + k;
-      if (L.active && gi < a.Nx && j < a.Ny) a.Gpart[((size_t)L.cid * a.Nx + gi) * a.Ny + j] = G[r][k];
+      if (L.active && gi < a.Nx && j < a.Ny) {
+        float* gp = a.Gpart + ((size_t)L.cid * a.Nx + gi) * a.Ny + j;
+        *gp = (CHAIN && a.accumulate) ? *gp + G[r][k] : G[r][k];
+      }
     }
   if (a.C > 1) cg::this_cluster().sync();
 }
@@ -454,6 +506,29 @@ static int max_threads_for(int R) {
     case 8: return 256;
     default: return 0;
   }
+}
+
+// ---- on-chip checkpoint-and-recompute (linear kernels) ---------------------------------------------------------------
+// wt_problem.checkpoint_every = S: the forward keeps no tape; every S steps (rounded up to a multiple of the TB = 64 step
+// staging block) each thread stores its register patch (u_{t-1}, u_{t-2}).  The backward walks the segments in reverse:
+// re-run the segment from its snapshot WITH a tape (which lives for one segment only), then run the adjoint over it, the
+// pair (P_{t-1}, P_t) passing from launch to launch.  Memory: B*T*4 (x) + (T/S - 1) snapshots of 2 fields + S tape steps,
+// instead of T tape steps.
+static int ckpt_interval(const wt_problem* p) {
+  if (p->checkpoint_every <= 0 || nonlinear_mask(p) || !(p->flags & WT_F_ZERO_INIT)) return 0;
+  const int S = round_up(p->checkpoint_every, TB);
+  return S < p->T ? S : 0;
+}
+struct CkptLayout { int n_seg; size_t x_bytes, patch, snaps, tape, total; };
+static CkptLayout ckpt_layout(const wt_problem* p, int C, int R, int threads, int S) {
+  CkptLayout l;
+  l.n_seg = (p->T + S - 1) / S;
+  l.x_bytes = ((size_t)p->B * p->T * 4 + 255) & ~(size_t)255;
+  l.patch = (size_t)p->B * C * 2 * R * threads * 16;          // one snapshot (or the chain pair) of the whole batch
+  l.snaps = l.patch * (l.n_seg - 1);
+  l.tape = (size_t)p->B * S * C * R * threads * 16;
+  l.total = l.x_bytes + l.snaps + l.tape;
+  return l;
 }
 
 template <typename K>
@@ -617,6 +692,18 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
   plan->history_bytes = (uint64_t)p->B * p->T * bestC * (nl ? 2 : 1) * bestR * threads * 16;
   plan->workspace_fwd_bytes = 3 * plane * 4 + 64;
   plan->workspace_bwd_bytes = (3 + 2 * (size_t)plan->n_clusters) * plane * 4 + 64;
+  plan->reserved[2] = 0;
+  const int S = ckpt_interval(p);
+  if (S) {
+    // checkpoint-and-recompute on chip: history = [x copy][register-patch snapshots every S steps][tape of ONE segment]
+    const CkptLayout lay = ckpt_layout(p, bestC, bestR, threads, S);
+    plan->reserved[2] = S;
+    plan->history_bytes = lay.total;
+    plan->workspace_bwd_bytes += lay.patch + 256;       // the (P_{t-1}, P_t) pair handed from segment to segment
+    plan->launches_fwd = 3;
+    plan->launches_bwd = 2 * lay.n_seg + 2;
+    return true;
+  }
   plan->launches_fwd = nl ? 1 : 2;
   plan->launches_bwd = 3;
   return true;
@@ -696,6 +783,18 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
   a.tape = reinterpret_cast<float4*>(history);
   a.status = status;
   if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st);
+  if (plan.reserved[2] && history) {   // checkpoint-and-recompute: no tape, snapshots every S steps, x kept for the recompute
+    if (a.fields) { wt::set_error("wt_forward: fields_out together with history needs WT_F_FORCE_STREAM"); return WT_EUNSUPPORTED; }
+    const CkptLayout lay = ckpt_layout(p, plan.cluster, plan.rows_per_thread, plan.threads, plan.reserved[2]);
+    char* hb = reinterpret_cast<char*>(history);
+    WT_CUDA(cudaMemcpyAsync(hb, x, (size_t)p->B * p->T * 4, cudaMemcpyDeviceToDevice, st));
+    a.tape = nullptr;
+    a.Tstride = p->T; a.t_off = 0; a.snap_every = plan.reserved[2];
+    a.snap = reinterpret_cast<float4*>(hb + lay.x_bytes);
+    a.snap_in = nullptr;
+    WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, false, 0, 0, false, true>, plan, plan.smem_fwd, a, st)));
+    return WT_OK;
+  }
   if (!a.fields && !(a.flags & WT_F_NO_SPECIALIZE)) {
 #define WT_SPEC_F(R_, P_, N_, G_)                                                                       \
     if (plan.rows_per_thread == R_ && a.pitch == P_ && plan.threads == N_) {                              \
@@ -745,6 +844,33 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
     k_finish_grad<<<fg, 256, 0, st>>>(Gpart, nullptr, plan.n_clusters, 2 * plane, plane, grad_c);
     if (grad_rho) k_finish_grad<<<fg, 256, 0, st>>>(Gpart + plane, nullptr, plan.n_clusters, 2 * plane, plane, grad_rho);
     if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));   // needs WT_F_NEED_GRAD_B (streaming path)
+    WT_CUDA(cudaGetLastError());
+    return WT_OK;
+  }
+  if (plan.reserved[2]) {   // checkpoint-and-recompute: per segment, newest first: forward from its snapshot with a tape, adjoint
+    const int S = plan.reserved[2];
+    const CkptLayout lay = ckpt_layout(p, plan.cluster, plan.rows_per_thread, plan.threads, S);
+    char* hb = reinterpret_cast<char*>(const_cast<void*>(history));
+    float4* snaps = reinterpret_cast<float4*>(hb + lay.x_bytes);
+    float4* tape = reinterpret_cast<float4*>(hb + lay.x_bytes + lay.snaps);
+    float4* chain = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(status + 1) + 255) & ~(uintptr_t)255);
+    for (int k = lay.n_seg - 1; k >= 0; --k) {
+      const int t0 = k * S, len = (p->T - t0 < S) ? p->T - t0 : S;
+      ResArgs f = a;
+      f.T = len; f.Tstride = p->T; f.t_off = t0; f.snap_every = 0; f.snap = nullptr;
+      f.snap_in = k > 0 ? snaps + (size_t)(k - 1) * (lay.patch / 16) : nullptr;
+      f.x = reinterpret_cast<const float*>(hb);
+      f.u1 = f.u2 = nullptr; f.probe_out = nullptr; f.probe_raw = nullptr; f.fields = nullptr; f.grad_x = nullptr;
+      f.tape = tape;
+      WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, true, 0, 0, false, true>, plan, plan.smem_fwd, f, st)));
+      ResArgs g = a;
+      g.T = len; g.Tstride = p->T; g.t_off = t0; g.tape = tape; g.chain = chain;
+      g.chain_in = k < lay.n_seg - 1; g.chain_out = k > 0; g.accumulate = k < lay.n_seg - 1;
+      WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R, 0, 0, 1, 0, true>, plan, plan.smem_bwd, g, st)));
+    }
+    k_finish_grad_p<<<fg, 256, 0, st>>>(Gpart, c, plan.n_clusters, plane, plane, grad_c);
+    if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
+    if (grad_rho) WT_CUDA(cudaMemsetAsync(grad_rho, 0, plane * sizeof(float), st));
     WT_CUDA(cudaGetLastError());
     return WT_OK;
   }

@@ -43,6 +43,15 @@ struct ResArgs {
   const float* rho;
   int ring;                  // tape prefetch depth
   Scalars s;
+  // on-chip checkpoint-and-recompute (CKPT / CHAIN instantiations of the linear kernels): this launch covers the steps
+  // [t_off, t_off + T) of sequences of Tstride steps
+  int Tstride, t_off;
+  int snap_every;            // forward: store my (u_{t-1}, u_{t-2}) patch whenever t_off + t is a positive multiple of this
+  float4* snap;              // [n_seg-1][B][C][2R][NT] snapshots, thread-major like the tape
+  const float4* snap_in;     // [B][C][2R][NT] initial state of this launch (NULL: zero fields)
+  float4* chain;             // adjoint: [B][C][2R][NT] (P_{t-1}, P_t) at the segment boundary, read and/or written
+  int chain_in, chain_out;   // this launch continues a later segment / is continued by an earlier one
+  int accumulate;            // Gpart += instead of =
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -51,6 +51,7 @@ class LoopSpec:
     checkpoint_every: int = 0   # > 0: keep only (u_t, u_{t-1}) every S steps and recompute each segment's tape in backward
     batch_chunk: int = 0        # > 0: process the batch in chunks of this many waveforms (bounds the tape / checkpoints)
     track_grad: bool = True     # grad mode of the caller (Function.forward itself always runs with grad disabled)
+    onchip_ckpt: int = 0        # set by wave_rnn: checkpoint interval handled inside the on-chip kernels (wt_problem.checkpoint_every)
 
 
 def _call_forward(lib, prob, dev, c32, b32, rho32, x32, spec, u1, u2, probe_out, probe_raw, fields, hist, ws):
@@ -228,6 +229,8 @@ class _WaveLoop(torch.autograd.Function):
         prob = _lib.make_problem(Nx, Ny, B, T, n_src, n_prb, spec.dt, spec.h, spec.b0, spec.uth, spec.c_nl, flags,
                                  dev.index if dev.index is not None else torch.cuda.current_device(), spec.cluster,
                                  spec.rows_per_thread)
+        if spec.onchip_ckpt and want_grad:
+            prob.checkpoint_every = int(spec.onchip_ckpt)
         fe = int(spec.field_every) if spec.output_fields else 1
         if fe > 1:
             if want_grad:
@@ -303,6 +306,17 @@ def wave_rnn(x, c, b, rho, spec):
     spec.track_grad = torch.is_grad_enabled()
     T = x.shape[1]
     chunked = bool(spec.batch_chunk) and 0 < spec.batch_chunk < x.shape[0]
+    if spec.checkpoint_every and 0 < spec.checkpoint_every < T and not chunked and not spec.output_fields and c.is_cuda:
+        # small grids: checkpoint-and-recompute inside the on-chip kernels (snapshots of the register patches, a tape that
+        # lives for one segment) when the planner puts this problem on that path; otherwise the segment loop below
+        prob = _lib.make_problem(c.shape[0], c.shape[1], x.shape[0], T, spec.src_ij.shape[0], spec.prb_ij.shape[0], spec.dt,
+                                 spec.h, spec.b0, spec.uth, spec.c_nl, spec.flags | _lib.WT_F_ZERO_INIT,
+                                 _dev_index(c.device), spec.cluster, spec.rows_per_thread)
+        prob.checkpoint_every = int(spec.checkpoint_every)
+        plan = _lib.query_plan(prob)
+        if plan.path == _lib.WT_PATH_RESIDENT and plan.reserved[2] > 0:
+            spec.onchip_ckpt = int(spec.checkpoint_every)
+            return _WaveLoop.apply(x, c, b, rho, spec)
     if (spec.checkpoint_every and 0 < spec.checkpoint_every < T) or (chunked and T > 0 and not spec.output_fields):
         if not spec.checkpoint_every or spec.checkpoint_every >= T:
             spec.checkpoint_every = T      # batch chunks without time checkpoints: one segment per chunk
