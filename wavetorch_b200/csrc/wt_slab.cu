@@ -61,27 +61,36 @@ __global__ void __launch_bounds__(256) k_slab_exchange(XchgArgs a) {
   const long long n_up = a.up ? per_dir : 0, n_dn = a.dn ? per_dir : 0;
   const long long total = 2 * (n_up + n_dn);         // two fields
   typedef typename std::conditional<VEC == 4, float4, float>::type V;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int fld = (int)(i & 1);
-    long long k = i >> 1;
+  // element i -> (field, direction, sample, row, column vector); consecutive threads take consecutive vectors of a row
+  auto locate = [&](long long i, const V*& sp, V*& dp) {
+    const int fld = (int)(i / (n_up + n_dn));
+    long long k = i - (long long)fld * (n_up + n_dn);
     const bool to_up = k < n_up;
     if (!to_up) k -= n_up;
     const int col = (int)(k % rowv);
     const int row = (int)((k / rowv) % a.halo);
     const int b = (int)(k / ((long long)rowv * a.halo));
     const float* src = fld ? a.f2 : a.f1;
-    float* dst;
-    size_t so, dof;
     if (to_up) {
-      so = ((size_t)b * a.Nx + a.up + row) * a.Ny;
-      dof = ((size_t)b * a.up_Nx + (a.up_Nx - a.halo) + row) * a.Ny;
-      dst = fld ? a.up2 : a.up1;
+      sp = reinterpret_cast<const V*>(src + ((size_t)b * a.Nx + a.up + row) * a.Ny) + col;
+      dp = reinterpret_cast<V*>((fld ? a.up2 : a.up1) + ((size_t)b * a.up_Nx + (a.up_Nx - a.halo) + row) * a.Ny) + col;
     } else {
-      so = ((size_t)b * a.Nx + (a.Nx - a.dn - a.halo) + row) * a.Ny;
-      dof = ((size_t)b * a.dn_Nx + row) * a.Ny;
-      dst = fld ? a.dn2 : a.dn1;
+      sp = reinterpret_cast<const V*>(src + ((size_t)b * a.Nx + (a.Nx - a.dn - a.halo) + row) * a.Ny) + col;
+      dp = reinterpret_cast<V*>((fld ? a.dn2 : a.dn1) + ((size_t)b * a.dn_Nx + row) * a.Ny) + col;
     }
-    reinterpret_cast<V*>(dst + dof)[col] = reinterpret_cast<const V*>(src + so)[col];
+  };
+  // four independent loads in flight per thread before the first remote store: NVLink needs megabytes in flight
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 4 * stride) {
+    const V* sp[4];
+    V* dp[4];
+    V val[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < total) { locate(i + u * stride, sp[u], dp[u]); val[u] = *sp[u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < total) *dp[u] = val[u];
   }
   __threadfence_system();
   __syncthreads();
@@ -121,8 +130,8 @@ int slab_exchange(const wt_slab* s, int B, int Nx, int Ny, float* f1, float* f2,
   a.flags = s->flags; a.state = s->state;
   const bool v4 = Ny % 4 == 0 && !(((uintptr_t)f1 | (uintptr_t)f2 | s->up_f1 | s->up_f2 | s->dn_f1 | s->dn_f2) & 15);
   const long long total = 2LL * B * s->halo * (Ny / (v4 ? 4 : 1)) * ((s->up ? 1 : 0) + (s->dn ? 1 : 0));
-  int blocks = (int)((total + 256 * 8 - 1) / (256 * 8));   // all blocks wait in step 2: keep the grid small and co-resident
-  if (blocks > 64) blocks = 64;
+  int blocks = (int)((total + 256 * 8 - 1) / (256 * 8));   // all blocks wait in step 2: keep the grid co-resident (<= 1 per SM)
+  if (blocks > 128) blocks = 128;
   if (blocks < 1) blocks = 1;
   if (v4) k_slab_exchange<4><<<blocks, 256, 0, st>>>(a);
   else k_slab_exchange<1><<<blocks, 256, 0, st>>>(a);

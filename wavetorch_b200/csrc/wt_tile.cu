@@ -10,9 +10,19 @@
 //
 // HBM traffic per cell update: (2*E/O + 2)*4/K bytes for the fields (E/O = extended/owned cell ratio) instead of 12,
 // plus 4 for the tape when a gradient is wanted.  Coefficients are loaded once per tile and reused for every sample.
+//
+// Staging: the extended tile of the NEXT sample (both time levels) -- and, in the adjoint, the K tape tiles of its block --
+// are fetched by TMA tensor copies (cp.async.bulk.tensor.3d, SASS UTMALDG) issued by ONE thread while the current sample is
+// advanced: the tensor map describes the [B, Nx, Ny] field, the box is the extended tile, and everything the box covers
+// outside the domain is zero-filled by the copy engine -- which is exactly the reference's zero boundary (operators.py:11),
+// so no thread computes an address or a bounds predicate for the load.  Completion is counted on an mbarrier.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include <type_traits>
 
 #include "wt_common.cuh"
+#include "wt_resident_dev.cuh"
 #include "wt_slab.h"
 #include "wt_stream.h"
 #include "wt_tile.h"
@@ -43,19 +53,27 @@ struct TileArgs {
   float* probe_out;
   float* probe_raw;
   float* tape;        // nullable: [T][B][Nx*Ny] slots of L(u_{t-1}); this launch writes slots t0 .. t0+steps-1
+  // TMA descriptors: [B,Nx,Ny] views of U1 / U2 with the extended tile as box, [T*B,Nx,Ny] view of the tape with the owned tile
+  alignas(64) CUtensorMap tmU1;
+  alignas(64) CUtensorMap tmU2;
+  alignas(64) CUtensorMap tmTape;
 };
+
+// One box of a 3-D tensor map -> shared memory, completion on an mbarrier (c0 = column, c1 = row, c2 = sample / tape slot;
+// coordinates may be negative or overhang: those elements arrive as zeros)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 
 constexpr int TILE_MAX_PRB = 32;
 constexpr int TILE_MAX_K = 4;    // steps per launch: the step bodies are unrolled with a compile-time step index
 constexpr int TILE_ADJ_K = 4;   // the adjoint keeps K steps of tape staged per thread: fixed depth
 
-// Ampere-style asynchronous copies: every thread stages ITS OWN patch of the next sample (and, in the adjoint, its tape
-// rows) while the current one is being advanced, so the only exposed HBM latency is that of a CTA's first sample.
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool ok) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  const int n = ok ? 16 : 0;   // 0 source bytes: the 16 destination bytes are zero-filled, nothing is read
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
-}
+// x[b, t0 .. t0+steps) of the next sample: a handful of 4-byte asynchronous copies
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
@@ -103,14 +121,16 @@ __device__ __forceinline__ void tile_load_coef(const float* __restrict__ a1, con
 }
 
 template <int R>
-__global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd(TileArgs a) {
-  extern __shared__ float4 smem4[];
+__global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd(const __grid_constant__ TileArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int slab = (a.EH + 2) * a.pitch;
-  float* fld = reinterpret_cast<float*>(smem4);       // [2][slab], row 0 / EH+1 and the 4-float row pad stay zero
+  const int box = a.EH * a.EW;                         // floats in one staged extended tile
+  float* stg = reinterpret_cast<float*>(smem_raw);     // [2][EH][EW] the next sample's u_{t-1}, u_{t-2} (TMA destination)
+  float* fld = stg + 2 * box;                          // [2][slab], row 0 / EH+1 and the 4-float row pad stay zero
   float* xs = fld + 2 * slab;                          // [2][TILE_MAX_K], double-buffered over samples
   int* poff = reinterpret_cast<int*>(xs + 2 * TILE_MAX_K); // [TILE_MAX_PRB] smem offset of an owned probe
   int* pid = poff + TILE_MAX_PRB;                      // [TILE_MAX_PRB] its global index
-  float4* stg = reinterpret_cast<float4*>(pid + TILE_MAX_PRB);   // [2R][NT] staged patches of the next sample
+  uint64_t* bar = reinterpret_cast<uint64_t*>(pid + TILE_MAX_PRB);   // "staged tile has landed"
   __shared__ int n_my_prb;
 
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -125,17 +145,18 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
   const size_t plane = (size_t)a.Nx * a.Ny;
   const int b_lo = blockIdx.y * a.bchunk, b_hi = min(a.B, b_lo + a.bchunk);
 
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // ONE thread asks the copy engine for both time levels of sample b's extended tile; the zero boundary comes with it
   auto stage_sample = [&](int b) {
     if (b < b_hi) {
-      const float* u1p = a.U1 + (size_t)b * plane;
-      const float* u2p = a.U2 + (size_t)b * plane;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int gi = gi0 + r;
-        const bool ok = active && gi >= 0 && gi < a.Nx && gj0 >= 0 && gj0 + 3 < a.Ny;
-        const size_t o = ok ? (size_t)gi * a.Ny + gj0 : 0;
-        cp_async16(&stg[r * NT + tid], u1p + o, ok);
-        cp_async16(&stg[(R + r) * NT + tid], u2p + o, ok);
+      if (tid == 0) {
+        mbar_expect_tx(bar, 2u * (unsigned)box * 4u);
+        tma_load_3d(stg, &a.tmU1, tj0 - a.K, ti0 - a.K, b, bar);
+        tma_load_3d(stg + box, &a.tmU2, tj0 - a.K, ti0 - a.K, b, bar);
       }
       if (tid < a.steps) cp_async4(&xs[(b & 1) * TILE_MAX_K + tid], a.x + (size_t)b * a.T + a.t0 + tid);
     }
@@ -178,16 +199,19 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
   for (int r = 0; r < R; ++r) own_row[r] = col_in && lr0 + r >= a.K && lr0 + r < a.K + a.TH && gi0 + r < a.Nx;
   const long long row0 = (long long)gi0 * a.Ny + gj0;   // my first row inside a [Nx,Ny] plane (only used where own_row)
 
+  unsigned phase = 0;
+  const float4* my_stg = reinterpret_cast<const float4*>(stg + lr0 * a.EW + 4 * g);   // my patch inside a staged tile
   for (int b = b_lo; b < b_hi; ++b) {
     float v[R][4], w[R][4];
     cp_async_wait<0>();
+    mbar_wait(bar, phase);
+    phase ^= 1u;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const float4 p = stg[r * NT + tid], q = stg[(R + r) * NT + tid];
+      const float4 p = my_stg[r * (a.EW / 4)], q = my_stg[(box + r * a.EW) / 4];
       v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
       w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
     }
-    stage_sample(b + 1);   // lands while this sample is advanced
     const float* xsb = xs + (b & 1) * TILE_MAX_K;
     if (active) {
 #pragma unroll
@@ -195,6 +219,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, R <= 2 ? 2 : 1) k_tile_fwd
         *reinterpret_cast<float4*>(fld + (lr0 + r + 1) * a.pitch + 4 + 4 * g) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
     }
     __syncthreads();
+    stage_sample(b + 1);   // everybody has taken its patch out of the staging buffers: refill them while this sample is advanced
 
     // One step; J (the step inside the block) is a compile-time constant of each unrolled copy, so buffer parity and the
     // x slot are immediates.  `cu` = u_t (kept), `pr` = u_{t-1} on entry and u_{t+1} on exit.
@@ -276,19 +301,22 @@ struct TileAdjArgs {
 
 // GRADX: dLoss/dx is wanted (its gather is compiled out otherwise: the step body is fetched 2K times per tile)
 template <int R, bool GRADX>
-__global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs aa) {
+__global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(const __grid_constant__ TileAdjArgs aa) {
   const TileArgs& a = aa.g;
-  extern __shared__ float4 smem4[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int slab = (a.EH + 2) * a.pitch;
-  float* fld = reinterpret_cast<float*>(smem4);
+  const int box = a.EH * a.EW;                          // floats in one staged extended tile
+  const int tbox = (a.TH * a.TW + 31) & ~31;            // floats in one staged tape tile (slots stay 128-byte aligned)
+  float* stg = reinterpret_cast<float*>(smem_raw);      // [2][EH][EW] the next sample's P_t, P_{t+1} (TMA destination)
+  float* ring = stg + 2 * box;                          // [TILE_ADJ_K][TH][TW] its tape tiles, one slot per step of the block
+  float* fld = ring + TILE_ADJ_K * tbox;
   int* pown = reinterpret_cast<int*>(fld + 2 * slab);   // [TILE_MAX_PRB] owning thread of a probe inside the EXTENDED tile
   int* pcel = pown + TILE_MAX_PRB;                      // its cell index inside the owner's patch
   int* pid = pcel + TILE_MAX_PRB;                       // its global probe index
-  float4* stg = reinterpret_cast<float4*>(pid + TILE_MAX_PRB);   // [2R][NT] staged P_t, P_{t+1} patches of the next sample
+  uint64_t* bar = reinterpret_cast<uint64_t*>(pid + TILE_MAX_PRB);   // [1 + TILE_ADJ_K]: state tiles, tape tile of step j
   __shared__ int n_my_prb;
 
   const int tid = threadIdx.x, NT = blockDim.x;
-  float4* ring = stg + 2 * R * NT;                      // [TILE_ADJ_K][R][NT] staged tape rows, one slot per step of the block
   const bool active = tid < a.nact;
   const int run = tid / a.P4;
   const int g = tid - run * a.P4;
@@ -305,34 +333,29 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
   for (int r = 0; r < R; ++r) own_row[r] = col_in && lr0 + r >= a.K && lr0 + r < a.K + a.TH && gi0 + r < a.Nx;
   const long long row0 = (long long)gi0 * a.Ny + gj0;   // my first row inside a [Nx,Ny] plane (only used where own_row)
 
-  // copy group j of sample b: the tape rows of reverse step j, plus (j == 0) the two state patches.  Exactly TILE_ADJ_K
-  // groups are committed per sample, empty ones included, so that "at most K-1 groups pending" always means "the oldest
-  // one has landed".
-  auto stage = [&](int b, int j) {
-    if (b < b_hi) {
-      if (j == 0) {
-        const float* u1p = a.U1 + (size_t)b * plane;
-        const float* u2p = a.U2 + (size_t)b * plane;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int gi = gi0 + r;
-          const bool ok = active && gi >= 0 && gi < a.Nx && gj0 >= 0 && gj0 + 3 < a.Ny;
-          const size_t o = ok ? (size_t)gi * a.Ny + gj0 : 0;
-          cp_async16(&stg[r * NT + tid], u1p + o, ok);
-          cp_async16(&stg[(R + r) * NT + tid], u2p + o, ok);
-        }
-      }
-      if (j < a.steps && col_in) {
-        const float* tb = a.tape + ((size_t)(a.t0 - j) * a.B + b) * plane;
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          cp_async16(&ring[(j * R + r) * NT + tid], own_row[r] ? tb + row0 + r * a.Ny : tb, own_row[r]);
-      }
+  if (tid == 0) {
+    for (int j = 0; j <= TILE_ADJ_K; ++j) mbar_init(bar + j, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // TMA requests, all issued by thread 0: the two state tiles of sample b (extended tile, zero-filled outside the domain) ...
+  auto stage_state = [&](int b) {
+    if (tid == 0 && b < b_hi) {
+      mbar_expect_tx(bar, 2u * (unsigned)box * 4u);
+      tma_load_3d(stg, &a.tmU1, tj0 - a.K, ti0 - a.K, b, bar);
+      tma_load_3d(stg + box, &a.tmU2, tj0 - a.K, ti0 - a.K, b, bar);
     }
-    cp_async_commit();
   };
+  // ... and the tape tile (owned tile only) of its reverse step j
+  auto stage_tape = [&](int b, int j) {
+    if (tid == 0 && b < b_hi && j < a.steps) {
+      mbar_expect_tx(bar + 1 + j, (unsigned)(a.TH * a.TW) * 4u);
+      tma_load_3d(ring + j * tbox, &a.tmTape, tj0, ti0, (a.t0 - j) * a.B + b, bar + 1 + j);
+    }
+  };
+  stage_state(b_lo);
 #pragma unroll
-  for (int j = 0; j < TILE_ADJ_K; ++j) stage(b_lo, j);
+  for (int j = 0; j < TILE_ADJ_K; ++j) stage_tape(b_lo, j);
 
   float k1[R][4], k3[R][4];
   tile_load_coef<R>(a.a1, a.a3, active, gi0, gj0, a.Nx, a.Ny, k1, k3);
@@ -371,12 +394,16 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
 #pragma unroll
     for (int k = 0; k < 4; ++k) G[r][k] = 0.f;
 
+  unsigned phase = 0;      // every barrier completes exactly once per sample
+  const float4* my_stg = reinterpret_cast<const float4*>(stg + lr0 * a.EW + 4 * g);      // my patch inside a staged state tile
+  // my rows inside a staged tape tile (owned cells only: the tile starts K rows / K columns into the extended tile)
+  const float4* my_tape = reinterpret_cast<const float4*>(ring + (col_in ? (lr0 - a.K) * a.TW + (4 * g - a.K) : 0));
   for (int b = b_lo; b < b_hi; ++b) {
     float v[R][4], w[R][4];
-    cp_async_wait<TILE_ADJ_K - 1>();   // group 0 of this sample
+    mbar_wait(bar, phase);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const float4 p = stg[r * NT + tid], q = stg[(R + r) * NT + tid];
+      const float4 p = my_stg[r * (a.EW / 4)], q = my_stg[(box + r * a.EW) / 4];
       v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
       w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
     }
@@ -392,6 +419,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
         *reinterpret_cast<float4*>(fld + (lr0 + r + 1) * a.pitch + 4 + 4 * g) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
     }
     __syncthreads();
+    stage_state(b + 1);   // the staging buffers are free again: the next sample's state lands while this one is advanced
 
     // One reverse step; J (the step inside the block) is a compile-time constant of each unrolled copy: buffer parity and
     // ring slots are immediates.  cu = P_t (kept), pr = P_{t+1} (or the weighted carry) on entry and P_{t-1} on exit.
@@ -417,19 +445,20 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
         }
         atomicAdd(aa.grad_x + (size_t)b * a.T + t, sx);
       }
-      if (J > 0) cp_async_wait<TILE_ADJ_K - 1>();   // tape rows of this step
+      mbar_wait(bar + 1 + J, phase);   // tape tile of this step
       if (col_in) {
-        const float4* rs = ring + J * R * NT + tid;
+        const float4* rs = my_tape + (J * tbox) / 4;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const float4 tp = rs[r * NT];   // zero-filled where the row is not mine
-          G[r][0] = fmaf(tp.x, cu[r][0], G[r][0]);
-          G[r][1] = fmaf(tp.y, cu[r][1], G[r][1]);
-          G[r][2] = fmaf(tp.z, cu[r][2], G[r][2]);
-          G[r][3] = fmaf(tp.w, cu[r][3], G[r][3]);
+          if (own_row[r]) {
+            const float4 tp = rs[r * (a.TW / 4)];   // (zeros where the tile overhangs the domain)
+            G[r][0] = fmaf(tp.x, cu[r][0], G[r][0]);
+            G[r][1] = fmaf(tp.y, cu[r][1], G[r][1]);
+            G[r][2] = fmaf(tp.z, cu[r][2], G[r][2]);
+            G[r][3] = fmaf(tp.w, cu[r][3], G[r][3]);
+          }
         }
       }
-      stage(b + 1, J);   // refill the slots just consumed with the next sample's
       if (active) {
         float lap[R][4];
         patch_lap<R>(a.pitch, cur + own, cu, lap);
@@ -458,13 +487,12 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
           *reinterpret_cast<float4*>(nxt + own + r * a.pitch) = make_float4(pr[r][0], pr[r][1], pr[r][2], pr[r][3]);
       }
       __syncthreads();
+      stage_tape(b + 1, J);   // everybody has read this step's tape tile: refill the slot with the next sample's
     };
     auto body = [&](auto jc) {
       constexpr int J = decltype(jc)::value;
       if (J < a.steps) {
         if (J & 1) step(jc, w, v); else step(jc, v, w);
-      } else {
-        stage(b + 1, J);   // short last block: keep the group count per sample fixed
       }
     };
     body(std::integral_constant<int, 0>{});
@@ -472,6 +500,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
     body(std::integral_constant<int, 2>{});
     body(std::integral_constant<int, 3>{});
     static_assert(TILE_ADJ_K == 4, "the reverse steps are unrolled four times");
+    phase ^= 1u;
     const bool latest_in_v = (a.steps & 1) == 0;
     if (col_in) {   // owned tile back to HBM: V1 = P_{t_hi-steps}, V2 = P_{t_hi-steps+1}
       float* o1 = a.V1 + (size_t)b * plane + row0;
@@ -494,7 +523,6 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(TileAdjArgs 
     }
     __syncthreads();
   }
-  cp_async_wait<0>();
   if (col_in) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -548,6 +576,33 @@ size_t tile_extra_ws_bytes(const wt_problem* p) {
 
 struct TileGeom { int K, R, TH, TW, EH, EW, P4, pitch, runs, nact, threads, tiles_x, tiles_y; size_t smem; };
 
+// ---- TMA descriptors ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver; the runtime hands out its entry point (no -lcuda at link time).
+static PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+  }();
+  return fn;
+}
+// [n_planes, Nx, Ny] float32 tensor at `base`, box = box_h x box_w cells of one plane; out-of-range elements read as zero
+static int make_plane_map(CUtensorMap* tm, const float* base, size_t n_planes, int Nx, int Ny, int box_h, int box_w) {
+  PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return WT_EUNSUPPORTED; }
+  const cuuint64_t dims[3] = {(cuuint64_t)Ny, (cuuint64_t)Nx, (cuuint64_t)n_planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)Ny * 4, (cuuint64_t)Nx * Ny * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a %zux%dx%d tensor, box %dx%d", (int)r, n_planes, Nx, Ny, box_h, box_w); return WT_ECUDA; }
+  return WT_OK;
+}
+
 static TileGeom tile_geom(const wt_problem* p, int force_K = 0) {
   TileGeom t;
   t.K = TILE_MAX_K;   // K = 8 was measured slower (more halo work per useful cell)
@@ -568,7 +623,7 @@ static TileGeom tile_geom(const wt_problem* p, int force_K = 0) {
   t.threads = t.nact;
   t.tiles_x = (p->Nx + t.TH - 1) / t.TH;
   t.tiles_y = (p->Ny + t.TW - 1) / t.TW;
-  t.smem = (size_t)2 * (t.EH + 2) * t.pitch * 4 + 2 * TILE_MAX_K * 4 + 2 * TILE_MAX_PRB * 4 + (size_t)2 * t.R * t.threads * 16 + 64;
+  t.smem = (size_t)2 * t.EH * t.EW * 4 + (size_t)2 * (t.EH + 2) * t.pitch * 4 + 2 * TILE_MAX_K * 4 + 2 * TILE_MAX_PRB * 4 + 64 + 128;
   return t;
 }
 
@@ -595,11 +650,19 @@ int tile_forward(const wt_problem* p, const float* a1, const float* a3, const fl
   if (nby > p->B) nby = p->B;
   a.bchunk = (p->B + nby - 1) / nby;
   nby = (p->B + a.bchunk - 1) / a.bchunk;
+  // the two field pairs this call ping-pongs between, as [B,Nx,Ny] tensors with the extended tile as box
+  CUtensorMap mA1, mA2, mB1, mB2;
+  WT_TRY(make_plane_map(&mA1, A1, p->B, p->Nx, p->Ny, g.EH, g.EW));
+  WT_TRY(make_plane_map(&mA2, A2, p->B, p->Nx, p->Ny, g.EH, g.EW));
+  WT_TRY(make_plane_map(&mB1, B1, p->B, p->Nx, p->Ny, g.EH, g.EW));
+  WT_TRY(make_plane_map(&mB2, B2, p->B, p->Nx, p->Ny, g.EH, g.EW));
   int n = 0;
   for (int t0 = 0; t0 < p->T; t0 += g.K) {
     a.t0 = t0;
     a.steps = p->T - t0 < g.K ? p->T - t0 : g.K;
     a.U1 = A1; a.U2 = A2; a.V1 = B1; a.V2 = B2;
+    a.tmU1 = (A1 == u1) ? mA1 : mB1;
+    a.tmU2 = (A1 == u1) ? mA2 : mB2;
     dim3 grid(ntiles, nby), block(g.threads);
     switch (g.R) {
       case 2:
@@ -674,12 +737,22 @@ int tile_backward(const wt_problem* p, const float* a1, const float* a3, const f
   a.bchunk = (p->B + nby - 1) / nby;
   nby = (p->B + a.bchunk - 1) / a.bchunk;
   aa.atomic_G = nby > 1;
-  const size_t smem = (size_t)2 * (g.EH + 2) * g.pitch * 4 + 3 * TILE_MAX_PRB * 4 + (size_t)(2 + TILE_ADJ_K) * g.R * g.threads * 16 + 64;
+  const size_t tbox = ((size_t)g.TH * g.TW + 31) & ~(size_t)31;
+  const size_t smem = (size_t)2 * g.EH * g.EW * 4 + TILE_ADJ_K * tbox * 4 + (size_t)2 * (g.EH + 2) * g.pitch * 4 + 3 * TILE_MAX_PRB * 4 +
+                      (1 + TILE_ADJ_K) * 8 + 64 + 128;
   float* A1 = state1; float* A2 = state2; float* B1 = spare1; float* B2 = spare2;
+  CUtensorMap mA1, mA2, mB1, mB2;
+  WT_TRY(make_plane_map(&mA1, A1, p->B, p->Nx, p->Ny, g.EH, g.EW));
+  WT_TRY(make_plane_map(&mA2, A2, p->B, p->Nx, p->Ny, g.EH, g.EW));
+  WT_TRY(make_plane_map(&mB1, B1, p->B, p->Nx, p->Ny, g.EH, g.EW));
+  WT_TRY(make_plane_map(&mB2, B2, p->B, p->Nx, p->Ny, g.EH, g.EW));
+  WT_TRY(make_plane_map(&a.tmTape, tape, (size_t)p->T * p->B, p->Nx, p->Ny, g.TH, g.TW));   // owned tile of tape slot t*B + b
   for (int t_hi = p->T - 1; t_hi >= 0; t_hi -= g.K) {
     a.t0 = t_hi;
     a.steps = t_hi + 1 < g.K ? t_hi + 1 : g.K;
     a.U1 = A1; a.U2 = A2; a.V1 = B1; a.V2 = B2;
+    a.tmU1 = (A1 == state1) ? mA1 : mB1;
+    a.tmU2 = (A1 == state1) ? mA2 : mB2;
     aa.premul_first = aa.in_lambda = (t_hi == p->T - 1) ? 1 : 0;
     aa.out_lambda = (chained && t_hi - g.K < 0) ? 1 : 0;
     dim3 grid(ntiles, nby), block(g.threads);
