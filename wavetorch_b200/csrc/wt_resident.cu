@@ -58,12 +58,12 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
-    poff[p] = (li >= 0 && li < a.Hc) ? (li + 1) * pitch + 4 + pj : -1;
+    poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(pitch, li + 1, pj) : -1;
   }
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
   const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
-  const int own = (L.lr0 + 1) * pitch + 4 + L.j0;       // my first row inside a slab buffer
+  const int own = (L.lr0 + 1) * pitch + L.g;       // my first row inside a slab buffer
   const size_t tape_step = (size_t)a.C * R * NT;        // float4 per time step of one sample
   const size_t plane = (size_t)a.Nx * a.Ny;
 
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     if (pown[p] == tid) {
       if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
     }
-  const int own = (L.lr0 + 1) * pitch + 4 + L.j0;
+  const int own = (L.lr0 + 1) * pitch + L.g;
   const size_t tape_step = (size_t)a.C * R * NT;
   // the lane that re-issues tape copies sits in a middle warp: the first and last warps already wait for ghost rows
   const int refill_tid = ((NT / 32) / 2) * 32;

@@ -95,13 +95,20 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float x, float y, float z, float w, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(
-                   remote_addr),
-               "r"(__float_as_uint(x)), "r"(__float_as_uint(y)), "r"(__float_as_uint(z)), "r"(__float_as_uint(w)),
-               "r"(remote_bar)
+__device__ __forceinline__ void st_async_b32(uint32_t remote_addr, float x, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(x)), "r"(remote_bar)
                : "memory");
 }
+
+// ---- slab buffer layout --------------------------------------------------------------------------------------------
+// A slab row holds the 4*P4 cells of a grid row as FOUR PLANES of P4 + 1 words: cell c lives in plane c & 3 at index c >> 2
+// (the thread that owns columns 4g .. 4g+3 has one cell in each plane, all at index g), the extra word of every plane is
+// a zero pad.  Row pitch = 4 * (P4 + 1) words.  Why: every shared-memory access of the stencil becomes a 32-bit access
+// with consecutive lanes on consecutive words -- one wavefront -- including the left / right rim (plane 3 at g-1, plane 0
+// at g+1; for the first / last thread those are the zero pads, i.e. the zero boundary).  With the row-major layout the rim
+// loads were 32-bit loads 16 bytes apart, a 4-way bank conflict each, and made up 60 % of the kernel's wavefronts.
+__device__ __forceinline__ int slab_cell(int pitch, int row, int col) { return row * pitch + (col & 3) * (pitch >> 2) + (col >> 2); }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n"
@@ -119,7 +126,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity
 // Per-thread view of the decomposition and of the ghost exchange.
 template <int R>
 struct Lane {
-  int rank, cid, tid, run, j0, lr0, gi0, slab;
+  int rank, cid, tid, run, g, j0, lr0, gi0, slab;
   bool active;
   bool edge_up, edge_dn;     // my patch borders the slab of rank-1 / rank+1
   bool arm_up, arm_dn;       // I re-arm the corresponding mbarrier
@@ -138,7 +145,8 @@ struct Lane {
     tid = threadIdx.x;
     active = tid < a.nact;
     run = tid / a.P4;
-    j0 = 4 * (tid - run * a.P4);
+    g = tid - run * a.P4;
+    j0 = 4 * g;
     lr0 = run * R;
     gi0 = rank * a.Hc + lr0;
     slab = (a.Hc + 2) * a.pitch;
@@ -151,11 +159,11 @@ struct Lane {
     arm_dn = edge_dn && j0 == 0;
     push_up = push_dn = rbar_up = rbar_dn = 0;
     if (edge_up) {   // my top row is the ghost row BELOW the last row of rank-1
-      push_up = mapa_u32(smem_u32(fld + (a.Hc + 1) * a.pitch + 4 + j0), rank - 1);
+      push_up = mapa_u32(smem_u32(fld + (a.Hc + 1) * a.pitch + g), rank - 1);
       rbar_up = mapa_u32(smem_u32(bars + 2), rank - 1);
     }
     if (edge_dn) {   // my bottom row is the ghost row ABOVE the first row of rank+1
-      push_dn = mapa_u32(smem_u32(fld + 4 + j0), rank + 1);
+      push_dn = mapa_u32(smem_u32(fld + g), rank + 1);
       rbar_dn = mapa_u32(smem_u32(bars + 0), rank + 1);
     }
     if (tid == 0) {
@@ -169,14 +177,22 @@ struct Lane {
   // Write my R rows into slab buffer `which` (0/1) and push the rim rows to the neighbours.
   // pitch: a.pitch, or the same value as a compile-time constant in the shape-specialised kernels
   __device__ __forceinline__ void publish(int pitch, float* fld, int which, const float (&v)[R][4]) {
-    float* buf = fld + which * slab + (lr0 + 1) * pitch + 4 + j0;
+    const int PS = pitch >> 2;
+    float* buf = fld + which * slab + (lr0 + 1) * pitch + g;
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      *reinterpret_cast<float4*>(buf + r * pitch) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) buf[r * pitch + k * PS] = v[r][k];
     const uint32_t boff = (uint32_t)(which * slab) * 4u;
     const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
-    if (edge_up) st_async_v4(push_up + boff, v[0][0], v[0][1], v[0][2], v[0][3], rbar_up + bsel);
-    if (edge_dn) st_async_v4(push_dn + boff, v[R - 1][0], v[R - 1][1], v[R - 1][2], v[R - 1][3], rbar_dn + bsel);
+    if (edge_up) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st_async_b32(push_up + boff + (uint32_t)(k * PS) * 4u, v[0][k], rbar_up + bsel);
+    }
+    if (edge_dn) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st_async_b32(push_dn + boff + (uint32_t)(k * PS) * 4u, v[R - 1][k], rbar_dn + bsel);
+    }
   }
 
   // Wait until the neighbours' rows of the latest publish have landed in my ghost rows; re-arm for the next one.
@@ -230,14 +246,17 @@ __device__ __forceinline__ void load_coef(const ResArgs& a, bool active, int gi0
 // Unscaled 5-point Laplacian of my patch; own cells come from registers, the rim from shared memory.
 template <int R>
 __device__ __forceinline__ void patch_laplacian(int pitch, const float* own, const float (&v)[R][4], float (&lap)[R][4]) {
-  // `own` points at my first row inside the slab buffer
-  const float4 up = *reinterpret_cast<const float4*>(own - pitch);
-  const float4 dn = *reinterpret_cast<const float4*>(own + R * pitch);
-  const float upv[4] = {up.x, up.y, up.z, up.w};
-  const float dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+  // `own` points at plane 0 of my first row inside the slab buffer (slab_cell layout)
+  const int PS = pitch >> 2;
+  float upv[4], dnv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    upv[k] = own[k * PS - pitch];
+    dnv[k] = own[k * PS + R * pitch];
+  }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const float lf = own[r * pitch - 1], rt = own[r * pitch + 4];
+    const float lf = own[r * pitch + 3 * PS - 1], rt = own[r * pitch + 1];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float n = (r == 0) ? upv[k] : v[r - 1][k];
