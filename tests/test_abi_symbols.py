@@ -60,12 +60,15 @@ def test_struct_offsets_match_the_header_as_compiled_by_gcc(tmp_path):
     from wavetorch_b200 import _lib
     if shutil.which("gcc") is None:
         pytest.skip("no gcc")
+    from wavetorch_b200.domain import WtSlab
     fields_p = [f[0] for f in _lib.WtProblem._fields_]
     fields_q = [f[0] for f in _lib.WtPlan._fields_]
+    fields_s = [f[0] for f in WtSlab._fields_]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "wavetorch_b200.h"', 'int main(void) {',
-           '  printf("%zu %zu\\n", sizeof(wt_problem), sizeof(wt_plan));']
+           '  printf("%zu %zu %zu\\n", sizeof(wt_problem), sizeof(wt_plan), sizeof(wt_slab));']
     src += ['  printf("%%zu\\n", offsetof(wt_problem, %s));' % f for f in fields_p]
     src += ['  printf("%%zu\\n", offsetof(wt_plan, %s));' % f for f in fields_q]
+    src += ['  printf("%%zu\\n", offsetof(wt_slab, %s));' % f for f in fields_s]
     src += ['  return 0;', '}']
     c = tmp_path / "layout.c"
     c.write_text("\n".join(src))
@@ -73,6 +76,8 @@ def test_struct_offsets_match_the_header_as_compiled_by_gcc(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == ctypes.sizeof(_lib.WtProblem) and int(out[1]) == ctypes.sizeof(_lib.WtPlan)
-    offs = [int(v) for v in out[2:]]
-    expect = [getattr(_lib.WtProblem, f).offset for f in fields_p] + [getattr(_lib.WtPlan, f).offset for f in fields_q]
+    assert int(out[2]) == ctypes.sizeof(WtSlab)
+    offs = [int(v) for v in out[3:]]
+    expect = [getattr(_lib.WtProblem, f).offset for f in fields_p] + [getattr(_lib.WtPlan, f).offset for f in fields_q] + \
+             [getattr(WtSlab, f).offset for f in fields_s]
     assert offs == expect

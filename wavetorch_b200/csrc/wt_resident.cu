@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 if (bit == r * 4 + k) { cv = cu[r][k]; kv = k3[r][k]; }
-            const float q = kv != 0.f ? cv / kv : 0.f;   // a cell with c == 0 carries no P (INTEGRATION.md section 6)
+            const float q = kv != 0.f ? cv / kv : 0.f;   // a cell with c == 0 carries no P (INTEGRATION.md section 7)
             s += q;
             if (m2 >> bit & 1u) s += q;
           }

@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(R <= 2 ? 512 : 384, 1) k_tile_adj(const __grid
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (bit == r * 4 + k) { cv = cu[r][k]; kv = k3[r][k]; }
-          const float q = kv != 0.f ? cv / kv : 0.f;   // c == 0: the cell carries no P (INTEGRATION.md section 6)
+          const float q = kv != 0.f ? cv / kv : 0.f;   // c == 0: the cell carries no P (INTEGRATION.md section 7)
           sx += q;
           if (m2 >> bit & 1u) sx += q;
           if (m3 >> bit & 1u) sx += q;
