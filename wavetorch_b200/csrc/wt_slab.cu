@@ -14,6 +14,8 @@
 // The epoch lives in device memory: the whole time loop, exchanges included, is plain stream work (CUDA-graph capturable).
 // Traffic per exchange and neighbour: 2 fields x halo rows x Ny x B x 4 bytes in each direction (4.2 MB at config 5, B = 8),
 // against ~1 GB of HBM traffic for the 16 time steps in between.
+#include <stdlib.h>
+
 #include "wt_slab.h"
 
 namespace wt {
@@ -121,6 +123,9 @@ int slab_check(const wt_slab* s, int B, int Nx, int Ny) {
 
 int slab_exchange(const wt_slab* s, int B, int Nx, int Ny, float* f1, float* f2, cudaStream_t st) {
   if (!s || (!s->up && !s->dn)) return WT_OK;
+  // WT_SLAB_SKIP=1 (measurement only, results are WRONG): leave the exchange out to see what it costs in situ
+  static const bool skip = [] { const char* e = getenv("WT_SLAB_SKIP"); return e && e[0] == '1'; }();
+  if (skip) return WT_OK;
   XchgArgs a = {};
   a.B = B; a.Nx = Nx; a.Ny = Ny; a.halo = s->halo; a.up = s->up; a.dn = s->dn; a.up_Nx = s->up_Nx; a.dn_Nx = s->dn_Nx;
   a.f1 = f1; a.f2 = f2;
