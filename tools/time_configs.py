@@ -30,6 +30,10 @@ report("1/2 lens 151x151 B=1 T=500", m, x, torch.tensor([2], device="cuda"), 151
 for B, T in ((64, 1000), (8, 1000), (64, 5469)):
     m = _vowel_model(); x = torch.tensor(wo.synthetic_vowels(B, T), device="cuda")
     report(f"3 vowel 150x100 B={B} T={T}", m, x, torch.arange(B, device="cuda") % 3, B * T * 15000, 150, 100)
+m = _vowel_model(); m.checkpoint_every = 128; x = torch.tensor(wo.synthetic_vowels(64, 1000), device="cuda")
+report("3 vowel B=64 T=1000, on-chip checkpoints every 128", m, x, torch.arange(64, device="cuda") % 3, 64 * 1000 * 15000, 150, 100)
+m = _vowel_model(); m.checkpoint_every = 256; x = torch.tensor(wo.synthetic_vowels(64, 5469), device="cuda")
+report("3 vowel B=64 T=5469, on-chip checkpoints every 256", m, x, torch.arange(64, device="cuda") % 3, 64 * 5469 * 15000, 150, 100)
 for name, nl, T in (("4(i) satdamp b0=.1 uth=1", (0.1, 1.0, 0.0), 3000), ("4(ii) satdamp+kerr", (0.1, 1.0, -30.0), 1000), ("4(iii) satdamp uth=1.8e-4", (0.1, 0.00018, 0.0), 1000)):
     B = 64
     m = _vowel_model(*nl); x = torch.tensor(wo.synthetic_vowels(B, T), device="cuda")
