@@ -76,7 +76,7 @@ typedef struct wt_problem {
   int32_t rows_per_thread;
   int32_t field_every; /* fields_out keeps every field_every-th field only (0 or 1 = all): snapshot k is the field after
                           step (k+1)*field_every - 1, k < T / field_every.  Forward/inference only. */
-  int32_t checkpoint_every; /* > 0, on-chip path, linear cell, WT_F_ZERO_INIT: checkpoint-and-recompute.  wt_forward writes no
+  int32_t checkpoint_every; /* > 0, on-chip path (linear or nonlinear cell), WT_F_ZERO_INIT: checkpoint-and-recompute.  wt_forward writes no
                           tape; it stores the field pair every checkpoint_every steps (rounded up to a multiple of 64) into
                           `history`, and wt_backward re-runs each segment with a tape that lives for one segment only.
                           plan.history_bytes shrinks from T to about checkpoint_every + 2*T/checkpoint_every field copies;

@@ -1039,3 +1039,41 @@ def test_onchip_checkpoint_and_recompute(B, T, S, cluster, rows):
         xg = torch.tensor(g["x_f64"], dtype=torch.float32, device=DEV)
         _loss_head(m(xg), torch.arange(6, device=DEV) % 3).backward()
         assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f32"]) < 1e-4
+
+
+@pytest.mark.parametrize("name,b0,uth,cnl,B,T,S", [("satdamp", 0.1, 1.0, 0.0, 5, 300, 64), ("kerr", 0.0, 1.0, -30.0, 4, 200, 128),
+                                                   ("both", 0.1, 1.0, -30.0, 6, 1000, 256), ("satdamp_uth", 0.1, 0.00018, 0.0, 3, 150, 64)])
+def test_onchip_checkpoint_and_recompute_nonlinear(name, b0, uth, cnl, B, T, S):
+    """Checkpoint-and-recompute on the on-chip path with saturable damping / Kerr terms (BASELINE config 4): the adjoint of a
+    segment needs u_{t-2} of its first step, which comes from the snapshot the segment was recomputed from.  Probes bitwise,
+    gradients (rho.grad through c AND through the direct nonlinear terms, x.grad) to the order of the per-segment sums;
+    ("both", B=6, T=1000) is the reference fixture vowel_both."""
+    m = _vowel_model(b0, uth, cnl)
+    x0 = wo.synthetic_vowels(B, T) * (0.05 if cnl != 0.0 and name != "both" else 1.0)
+    if name == "both":
+        x0 = load_golden("vowel_both")["x_f64"].astype(np.float32)
+    w = torch.tensor(np.random.RandomState(2).rand(B, T, 3), dtype=torch.float32, device=DEV)
+    x = torch.tensor(x0, device=DEV, requires_grad=True)
+    out_ref = m(x)
+    (out_ref * w).sum().backward()
+    g_ref, gx_ref = m.cell.geom.rho.grad.clone(), x.grad.clone()
+    m.zero_grad(); x.grad = None
+    m.checkpoint_every = S
+    p = _lib.make_problem(150, 100, B, T, 1, 3, 1.0, 1.4283556979968262, b0, uth, cnl, flags=_lib.WT_F_ZERO_INIT)
+    full = int(_lib.query_plan(p).history_bytes)
+    p.checkpoint_every = S
+    plan = _lib.query_plan(p)
+    assert plan.path == _lib.WT_PATH_RESIDENT and plan.reserved[2] == S and int(plan.history_bytes) < full
+    l0 = _lib.launch_count
+    out = m(x)
+    (out * w).sum().backward()
+    assert _lib.launch_count - l0 < 60
+    assert torch.equal(out.detach(), out_ref.detach())
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g_ref.cpu().numpy()) < 5e-6
+    assert rel_l2(x.grad.cpu().numpy(), gx_ref.cpu().numpy()) < 5e-6
+    if name == "both":
+        g = load_golden("vowel_both")
+        m.zero_grad()
+        _loss_head(m(x.detach()), torch.arange(6, device=DEV) % 3).backward()
+        floor_g = rel_l2(g["rho_grad_f32"], g["rho_grad_f64"])
+        assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f64"]) < max(1e-4, 3 * floor_g)

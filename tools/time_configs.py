@@ -34,6 +34,8 @@ m = _vowel_model(); m.checkpoint_every = 128; x = torch.tensor(wo.synthetic_vowe
 report("3 vowel B=64 T=1000, on-chip checkpoints every 128", m, x, torch.arange(64, device="cuda") % 3, 64 * 1000 * 15000, 150, 100)
 m = _vowel_model(); m.checkpoint_every = 256; x = torch.tensor(wo.synthetic_vowels(64, 5469), device="cuda")
 report("3 vowel B=64 T=5469, on-chip checkpoints every 256", m, x, torch.arange(64, device="cuda") % 3, 64 * 5469 * 15000, 150, 100)
+m = _vowel_model(0.1, 1.0, 0.0); m.checkpoint_every = 256; x = torch.tensor(wo.synthetic_vowels(64, 3000), device="cuda")
+report("4(i) satdamp B=64 T=3000, on-chip checkpoints every 256", m, x, torch.arange(64, device="cuda") % 3, 64 * 3000 * 15000, 150, 100, (0.1, 1.0, 0.0))
 for name, nl, T in (("4(i) satdamp b0=.1 uth=1", (0.1, 1.0, 0.0), 3000), ("4(ii) satdamp+kerr", (0.1, 1.0, -30.0), 1000), ("4(iii) satdamp uth=1.8e-4", (0.1, 0.00018, 0.0), 1000)):
     B = 64
     m = _vowel_model(*nl); x = torch.tensor(wo.synthetic_vowels(B, T), device="cuda")

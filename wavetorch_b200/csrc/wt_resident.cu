@@ -515,7 +515,7 @@ static int max_threads_for(int R) {
 // pair (P_{t-1}, P_t) passing from launch to launch.  Memory: B*T*4 (x) + (T/S - 1) snapshots of 2 fields + S tape steps,
 // instead of T tape steps.
 static int ckpt_interval(const wt_problem* p) {
-  if (p->checkpoint_every <= 0 || nonlinear_mask(p) || !(p->flags & WT_F_ZERO_INIT)) return 0;
+  if (p->checkpoint_every <= 0 || !(p->flags & WT_F_ZERO_INIT)) return 0;
   const int S = round_up(p->checkpoint_every, TB);
   return S < p->T ? S : 0;
 }
@@ -526,7 +526,7 @@ static CkptLayout ckpt_layout(const wt_problem* p, int C, int R, int threads, in
   l.x_bytes = ((size_t)p->B * p->T * 4 + 255) & ~(size_t)255;
   l.patch = (size_t)p->B * C * 2 * R * threads * 16;          // one snapshot (or the chain pair) of the whole batch
   l.snaps = l.patch * (l.n_seg - 1);
-  l.tape = (size_t)p->B * S * C * R * threads * 16;
+  l.tape = (size_t)p->B * S * C * R * threads * 16 * (nonlinear_mask(p) ? 2 : 1);   // nonlinear: u_{t-1} and L(u_{t-1})
   l.total = l.x_bytes + l.snaps + l.tape;
   return l;
 }
@@ -782,7 +782,7 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
   a.vec_fields = (p->Ny % 4 == 0) && (((uintptr_t)fields_out & 15) == 0);
   a.tape = reinterpret_cast<float4*>(history);
   a.status = status;
-  if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st);
+  if (plan.nonlinear && !(plan.reserved[2] && history)) return res_nl_launch_fwd(plan, a, st);
   if (plan.reserved[2] && history) {   // checkpoint-and-recompute: no tape, snapshots every S steps, x kept for the recompute
     if (a.fields) { wt::set_error("wt_forward: fields_out together with history needs WT_F_FORCE_STREAM"); return WT_EUNSUPPORTED; }
     const CkptLayout lay = ckpt_layout(p, plan.cluster, plan.rows_per_thread, plan.threads, plan.reserved[2]);
@@ -792,6 +792,7 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
     a.Tstride = p->T; a.t_off = 0; a.snap_every = plan.reserved[2];
     a.snap = reinterpret_cast<float4*>(hb + lay.x_bytes);
     a.snap_in = nullptr;
+    if (plan.nonlinear) return res_nl_launch_fwd(plan, a, st, true);
     WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, false, 0, 0, false, true>, plan, plan.smem_fwd, a, st)));
     return WT_OK;
   }
@@ -839,7 +840,7 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
   a.Gpart = Gpart; a.status = status;
   a.bpml = b; a.clin = c; a.rho = rho; a.s = make_scalars(p); a.ring = plan.reserved[0];
   const unsigned fg = (unsigned)((plane + 255) / 256);
-  if (plan.nonlinear) {
+  if (plan.nonlinear && !plan.reserved[2]) {
     WT_TRY(res_nl_launch_adj(plan, a, st));
     k_finish_grad<<<fg, 256, 0, st>>>(Gpart, nullptr, plan.n_clusters, 2 * plane, plane, grad_c);
     if (grad_rho) k_finish_grad<<<fg, 256, 0, st>>>(Gpart + plane, nullptr, plan.n_clusters, 2 * plane, plane, grad_rho);
@@ -862,11 +863,23 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
       f.x = reinterpret_cast<const float*>(hb);
       f.u1 = f.u2 = nullptr; f.probe_out = nullptr; f.probe_raw = nullptr; f.fields = nullptr; f.grad_x = nullptr;
       f.tape = tape;
-      WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, true, 0, 0, false, true>, plan, plan.smem_fwd, f, st)));
       ResArgs g = a;
-      g.T = len; g.Tstride = p->T; g.t_off = t0; g.tape = tape; g.chain = chain;
+      g.T = len; g.Tstride = p->T; g.t_off = t0; g.tape = tape; g.chain = chain; g.snap_in = f.snap_in;
       g.chain_in = k < lay.n_seg - 1; g.chain_out = k > 0; g.accumulate = k < lay.n_seg - 1;
-      WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R, 0, 0, 1, 0, true>, plan, plan.smem_bwd, g, st)));
+      if (plan.nonlinear) {
+        WT_TRY(res_nl_launch_fwd(plan, f, st, true));
+        WT_TRY(res_nl_launch_adj(plan, g, st, true));
+      } else {
+        WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, true, 0, 0, false, true>, plan, plan.smem_fwd, f, st)));
+        WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R, 0, 0, 1, 0, true>, plan, plan.smem_bwd, g, st)));
+      }
+    }
+    if (plan.nonlinear) {
+      k_finish_grad<<<fg, 256, 0, st>>>(Gpart, nullptr, plan.n_clusters, 2 * plane, plane, grad_c);
+      if (grad_rho) k_finish_grad<<<fg, 256, 0, st>>>(Gpart + plane, nullptr, plan.n_clusters, 2 * plane, plane, grad_rho);
+      if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));
+      WT_CUDA(cudaGetLastError());
+      return WT_OK;
     }
     k_finish_grad_p<<<fg, 256, 0, st>>>(Gpart, c, plan.n_clusters, plane, plane, grad_c);
     if (grad_b) WT_CUDA(cudaMemsetAsync(grad_b, 0, plane * sizeof(float), st));

@@ -280,7 +280,7 @@ int res_nl_max_threads_rt(int R);
 size_t res_nl_smem_fwd(int Hc, int pitch, int n_prb);
 size_t res_nl_smem_adj(int Hc, int pitch, int n_prb, int R, int threads, int ring);
 int res_nl_clusters(int R, int nl, int C, int threads, size_t smem_fwd, size_t smem_bwd);
-int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st);
-int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st);
+int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st, bool ckpt = false);
+int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st, bool chain = false);
 
 }  // namespace wt

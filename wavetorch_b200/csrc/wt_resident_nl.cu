@@ -53,7 +53,9 @@ __device__ __forceinline__ float rcp_fast(float x) {
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int R, bool SAT, bool KERR, bool FIELDS = false, int PITCH = 0, int NTC = 0>
+// CKPT: checkpoint-and-recompute instantiation (see k_res_fwd in wt_resident.cu): steps [t_off, t_off + T) of longer
+// sequences, optional start from a register-patch snapshot, snapshots every snap_every steps
+template <int R, bool SAT, bool KERR, bool FIELDS = false, int PITCH = 0, int NTC = 0, bool CKPT = false>
 __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs a) {
   extern __shared__ float4 smem4[];
   const int pitch = PITCH ? PITCH : a.pitch;
@@ -102,14 +104,25 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         int gi = L.gi0 + r, j = L.j0 + k;
-        bool ok = L.active && gi < a.Nx && j < a.Ny && !(a.flags & WT_F_ZERO_INIT);
+        bool ok = !CKPT && L.active && gi < a.Nx && j < a.Ny && !(a.flags & WT_F_ZERO_INIT);
         size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
         v[r][k] = ok ? a.u1[o] : 0.f;
         w[r][k] = ok ? a.u2[o] : 0.f;
       }
+    if (CKPT && a.snap_in) {   // resume from a snapshot: my own registers, as I stored them
+      const float4* sp = a.snap_in + ((size_t)b * a.C + L.rank) * 2 * R * NT + tid;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 p = sp[r * NT], q = sp[(R + r) * NT];
+        v[r][0] = p.x; v[r][1] = p.y; v[r][2] = p.z; v[r][3] = p.w;
+        w[r][0] = q.x; w[r][1] = q.y; w[r][2] = q.z; w[r][3] = q.w;
+      }
+    }
     if (L.active) L.publish(pitch, fld, 0, v);
     ++L.npub;
-    const float* xb = a.x + (size_t)b * a.T;
+    const int Tst = CKPT ? a.Tstride : a.T;
+    const int toff = CKPT ? a.t_off : 0;
+    const float* xb = a.x + (size_t)b * Tst + toff;
     for (int i = tid; i < TB && i < a.T; i += NT) xs[i] = xb[i];
     __syncthreads();
 
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
         int p = i % a.n_prb;
         if (poff[p] >= 0) {
           float val = src[i];
-          size_t o = ((size_t)b * a.T + t0 + i / a.n_prb) * a.n_prb + p;
+          size_t o = ((size_t)b * Tst + toff + t0 + i / a.n_prb) * a.n_prb + p;
           if (a.probe_raw) a.probe_raw[o] = val;
           if (a.probe_out) a.probe_out[o] = a.prb_sq[p] ? val * val : val;
         }
@@ -190,6 +203,14 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
         for (int i = tid; i < TB && t1 + i < a.T; i += NT) dst[i] = xb[t1 + i];
       }
       if (blk >= 2) flush(blk - 2);
+      if (CKPT && a.snap_every && t0 > 0 && (toff + t0) % a.snap_every == 0) {   // v = u_{t-1}, w = u_{t-2}: blocks are even
+        float4* sp = a.snap + ((((size_t)((toff + t0) / a.snap_every - 1) * a.B + b) * a.C + L.rank) * 2 * R) * NT + tid;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          sp[r * NT] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+          sp[(R + r) * NT] = make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
+        }
+      }
       int tt = 0;
       for (; tt + 1 < n; tt += 2) {
         step(v, w, t0 + tt, blk, tt);
@@ -212,7 +233,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         int gi = L.gi0 + r, j = L.j0 + k;
-        if (L.active && gi < a.Nx && j < a.Ny) {
+        if (L.active && gi < a.Nx && j < a.Ny && (!CKPT || a.u1)) {
           size_t o = ((size_t)b * a.Nx + gi) * a.Ny + j;
           a.u1[o] = v[r][k];
           a.u2[o] = w[r][k];
@@ -228,7 +249,10 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
 // =================================================================================================
 // PITCH / NTC: row pitch and threads per CTA as compile-time constants (0 = from the launch), see wt_resident.cu
 // GRADX = 0: dLoss/dx code compiled out (shape-specialised instances only); 1: decided at run time
-template <int R, bool SAT, bool KERR, int PITCH = 0, int NTC = 0, int GRADX = 1>
+// CHAIN: checkpoint-and-recompute instantiation: reverse steps of the segment [t_off, t_off + T); the carried pair
+// (lambda_{t-1} without its seeds, carry into lambda_{t-2}) passes from launch to launch through a.chain, u_{t-2} of the
+// segment's first step comes from the snapshot the segment started from (a.snap_in), gradient partials accumulate.
+template <int R, bool SAT, bool KERR, int PITCH = 0, int NTC = 0, int GRADX = 1, bool CHAIN = false>
 __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj_nl(ResArgs a) {
   const int NT = NTC ? NTC : blockDim.x;
   const int pitch = PITCH ? PITCH : a.pitch;
@@ -291,6 +315,17 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k) { lam[r][k] = 0.f; c2[r][k] = 0.f; }
+    if (CHAIN && a.chain_in) {
+      const float4* cp = a.chain + ((size_t)b * a.C + L.rank) * 2 * R * NT + tid;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 p = cp[r * NT], q = cp[(R + r) * NT];
+        lam[r][0] = p.x; lam[r][1] = p.y; lam[r][2] = p.z; lam[r][3] = p.w;
+        c2[r][0] = q.x; c2[r][1] = q.y; c2[r][2] = q.z; c2[r][3] = q.w;
+      }
+    }
+    const int Tst = CHAIN ? a.Tstride : a.T;
+    const int toff = CHAIN ? a.t_off : 0;
 
     auto tape_ptr = [&](int t) { return a.tape + ((((size_t)b * a.T + t) * a.C + L.rank) * 2 * R) * NT; };
     auto stage_seeds = [&](int blk) {
@@ -298,7 +333,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       float* dst = ss + (blk & 1) * TB * a.n_prb;
       for (int i = tid; i < n * a.n_prb; i += NT) {
         int p = i % a.n_prb;
-        size_t o = ((size_t)b * a.T + t0 + i / a.n_prb) * a.n_prb + p;
+        size_t o = ((size_t)b * Tst + toff + t0 + i / a.n_prb) * a.n_prb + p;
         float g = a.grad_probe[o];
         if (a.prb_sq[p]) g *= 2.f * a.probe_raw[o];
         dst[i] = g;
@@ -310,7 +345,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       for (int i = tid; i < n; i += NT) {
         float sv = src[i];
         src[i] = 0.f;
-        if (sv != 0.f) atomicAdd(a.grad_x + (size_t)b * a.T + t0 + i, sv);
+        if (sv != 0.f) atomicAdd(a.grad_x + (size_t)b * Tst + toff + t0 + i, sv);
       }
     };
     if (tid == 0) {
@@ -361,6 +396,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
           const float4 lpv = ring[slot * stage_f4 + (R + r) * NT + tid];
           float4 u2v = make_float4(0.f, 0.f, 0.f, 0.f);      // t = 0: u_{-2} is the zero initial field (WT_F_ZERO_INIT)
           if (t > 0) u2v = ring[slot2 * stage_f4 + r * NT + tid];
+          else if (CHAIN && a.snap_in) u2v = a.snap_in[(((size_t)b * a.C + L.rank) * 2 * R + R + r) * NT + tid];   // ... or the snapshot's u_{t-2}
           const float u1a[4] = {u1v.x, u1v.y, u1v.z, u1v.w};
           const float lpa[4] = {lpv.x, lpv.y, lpv.z, lpv.w};
           const float u2a[4] = {u2v.x, u2v.y, u2v.z, u2v.w};
@@ -436,6 +472,14 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       if (t == 0) step(P0{}, 0, it);
     }
     it_global += (unsigned)a.T;
+    if (CHAIN && a.chain_out) {
+      float4* cp = a.chain + ((size_t)b * a.C + L.rank) * 2 * R * NT + tid;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        cp[r * NT] = make_float4(lam[r][0], lam[r][1], lam[r][2], lam[r][3]);
+        cp[(R + r) * NT] = make_float4(c2[r][0], c2[r][1], c2[r][2], c2[r][3]);
+      }
+    }
     __syncthreads();
     if (GRADX && a.grad_x) flush_gx(0);
     __syncthreads();
@@ -448,8 +492,9 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
       int gi = L.gi0 + r, j = L.j0 + k;
       if (L.active && gi < a.Nx && j < a.Ny) {
         size_t o = ((size_t)L.cid * 2) * plane + (size_t)gi * a.Ny + j;
-        a.Gpart[o] = Gc[r][k];
-        a.Gpart[o + plane] = Gr[r][k];
+        const bool acc = CHAIN && a.accumulate;
+        a.Gpart[o] = acc ? a.Gpart[o] + Gc[r][k] : Gc[r][k];
+        a.Gpart[o + plane] = acc ? a.Gpart[o + plane] + Gr[r][k] : Gr[r][k];
       }
     }
   if (a.C > 1) cg::this_cluster().sync();
@@ -531,9 +576,14 @@ static int nl_launch(K kernel, const wt_plan& plan, size_t smem, const ResArgs& 
   return WT_OK;
 }
 
-int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
+int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st, bool ckpt) {
   const int R = plan.rows_per_thread, nl = plan.nonlinear;
   int rc = WT_EINVAL;
+  if (ckpt) {   // checkpoint-and-recompute instantiations (generic shapes)
+    WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR, false, 0, 0, true>, plan, plan.smem_fwd, a, st)))
+    if (rc == WT_EINVAL) set_error("nonlinear on-chip kernel R=%d nl=%d not instantiated", R, nl);
+    return rc;
+  }
   const bool spec = R == 2 && a.pitch == 104 && plan.threads == 480 && !(a.flags & WT_F_NO_SPECIALIZE);   // BASELINE config 4
   if (a.fields) {   // output_fields=True: separate instantiation, keeps the field stores out of the common step body
     WT_NL_ALL((rc = nl_launch(k_res_fwd_nl<RR, SAT, KERR, true>, plan, plan.smem_fwd, a, st)))
@@ -548,9 +598,14 @@ int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
   return rc;
 }
 
-int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st) {
+int res_nl_launch_adj(const wt_plan& plan, const ResArgs& a, cudaStream_t st, bool chain) {
   const int R = plan.rows_per_thread, nl = plan.nonlinear;
   int rc = WT_EINVAL;
+  if (chain) {
+    WT_NL_ALL((rc = nl_launch(k_res_adj_nl<RR, SAT, KERR, 0, 0, 1, true>, plan, plan.smem_bwd, a, st)))
+    if (rc == WT_EINVAL) set_error("nonlinear on-chip kernel R=%d nl=%d not instantiated", R, nl);
+    return rc;
+  }
   if (R == 2 && a.pitch == 104 && plan.threads == 480 && !(a.flags & WT_F_NO_SPECIALIZE)) {   // BASELINE config 4
     if (a.grad_x) {
       if (nl == 1) rc = nl_launch(k_res_adj_nl<2, true, false, 104, 480, 1>, plan, plan.smem_bwd, a, st);
