@@ -212,6 +212,22 @@ int wt_slab_backward(const wt_problem* p, const wt_slab* slab, const float* c, c
 int wt_slab_exchange(const wt_slab* slab, int B, int Nx, int Ny, float* f1, float* f2, int device, void* stream);
 
 /*
+ * float64 variants of wt_query_plan / wt_forward / wt_backward: the reference's utils.set_dtype('float64') mode
+ * (utils.py:14-20).  Same arguments with double fields; one launch per time step on the HBM-streaming kernels (linear and
+ * nonlinear cell), tape = every field; no adjoint-state chaining, no dLoss/dfields, no on-chip path.  They also serve as the
+ * on-GPU double-precision cross-check of the float32 kernels (tests/test_gpu_parity.py::test_float64_*).
+ */
+int wt_query_plan_f64(const wt_problem* p, wt_plan* plan);
+int wt_forward_f64(const wt_problem* p, const double* c, const double* b, const double* rho, const double* x,
+                   const int32_t* src_ij, const int32_t* prb_ij, const int32_t* prb_square, double* u1, double* u2,
+                   double* probe_out, double* probe_raw, double* fields_out, void* history, size_t history_bytes,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int wt_backward_f64(const wt_problem* p, const double* c, const double* b, const double* rho, const int32_t* src_ij,
+                    const int32_t* prb_ij, const int32_t* prb_square, const double* grad_probe, const double* probe_raw,
+                    const void* history, size_t history_bytes, double* grad_c, double* grad_b, double* grad_rho, double* grad_x,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * One leapfrog step without sources or probes: y = TimeStep.apply(b, c, y1, y2, dt, h).
  * b and c are [Nx,Ny] (b_batched / c_batched = 0) or [B,Nx,Ny] (= 1).  Uses p->Nx, Ny, B, dt, h, device.
  */

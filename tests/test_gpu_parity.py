@@ -343,10 +343,9 @@ def test_edge_cases():
     # inf/NaN propagate like the reference instead of being clamped (SURVEY B-9)
     xb = torch.zeros(1, 5, device=DEV); xb[0, 0] = float("inf")
     assert not torch.isfinite(m(xb, output_fields=True)).all()
-    # float64 input is accepted (cast) and returned as float64
-    with pytest.warns(UserWarning):
-        o64 = m(torch.zeros(1, 4, device=DEV, dtype=torch.float64))
-    assert o64.dtype == torch.float64
+    # float64 input to a float32 model: integrated in float64 (wt_forward_f64) and returned as float64
+    o64 = m(torch.zeros(1, 4, device=DEV, dtype=torch.float64))
+    assert o64.dtype == torch.float64 and o64.abs().max().item() == 0.0
 
 
 def test_wavecell_step_api_matches_rnn():
@@ -1077,3 +1076,69 @@ def test_onchip_checkpoint_and_recompute_nonlinear(name, b0, uth, cnl, B, T, S):
         _loss_head(m(x.detach()), torch.arange(6, device=DEV) % 3).backward()
         floor_g = rel_l2(g["rho_grad_f32"], g["rho_grad_f64"])
         assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f64"]) < max(1e-4, 3 * floor_g)
+
+
+# ------------------------------------------------------------------------------------------------
+# float64 mode (utils.set_dtype('float64'), utils.py:14-20): wt_forward_f64 / wt_backward_f64 against the reference's float64 runs
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def float64_default():
+    wt.utils.set_dtype("float64")
+    yield
+    wt.utils.set_dtype("float32")
+
+
+@pytest.mark.parametrize("name,b0,uth,cnl", [("small_linear", 0, 0, 0), ("small_satdamp", 0.4, 0.7, 0),
+                                             ("small_kerr", 0, 0, -0.12), ("small_both", 0.4, 0.7, -0.12)])
+def test_float64_small_cases(name, b0, uth, cnl, float64_default):
+    """A model built under set_dtype('float64') is integrated in float64 on the GPU: probes, rho.grad, x.grad and fields
+    against the float64 run of the unmodified reference at 1e-9 (the float32 path sits at 1e-5 / 1e-4)."""
+    g = load_golden(name)
+    geom = wt.WaveGeometryFreeForm((27, 22), 1.2, c0=1.0, c1=0.6, eta=0.5, beta=8.0, abs_sig=2.0, abs_N=3, abs_p=2.0,
+                                   rho=torch.tensor(g["rho_f64"]), blur_radius=1, blur_N=2, design_region=None)
+    cell = wt.WaveCell(0.8, geom, satdamp_b0=b0, satdamp_uth=uth, c_nl=cnl)
+    sources = [wt.WaveSource(6, 5), wt.WaveSource(6, 5), wt.WaveSource(9, 14)]
+    probes = [wt.WaveIntensityProbe(int(i), int(j)) if sq else wt.WaveProbe(int(i), int(j))
+              for (i, j), sq in zip(g["prb_xy"], g["prb_intensity"])]
+    m = wt.WaveRNN(cell, sources, probes).to(DEV)
+    assert m.cell.geom.rho.dtype == torch.float64
+    x = torch.tensor(g["x_f64"], device=DEV, requires_grad=True)
+    out = m(x)
+    assert out.dtype == torch.float64
+    (out * torch.tensor(g["w_f64"], device=DEV)).sum().backward()
+    assert rel_l2(m.cell.geom.c.detach().cpu().numpy(), g["c_f64"]) < 1e-13
+    assert rel_l2(out.detach().cpu().numpy(), g["out_f64"]) < 1e-9
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f64"]) < 1e-9
+    assert rel_l2(x.grad.cpu().numpy(), g["x_grad_f64"]) < 1e-9
+    with torch.no_grad():
+        fields = m(x.detach(), output_fields=True)
+    assert fields.dtype == torch.float64 and fields.shape == (3, 48, 27, 22)
+    assert rel_l2(fields[:, -1].cpu().numpy(), g["u_last_f64"]) < 1e-9
+    assert rel_l2(fields[:, 24].cpu().numpy(), g["u_mid_f64"]) < 1e-9
+
+
+def test_float64_config2_and_config4(float64_default):
+    """BASELINE config 2 (lens, B=1, T=500) and config 4 (ii) (saturable damping + Kerr, B=6, T=1000) in float64 against
+    the reference's float64 fixtures; and the float32 product path against THIS float64 GPU run (the on-GPU cross-check)."""
+    g = load_golden("lens_optimize")
+    m = _lens_model(0.5)
+    assert m.cell.geom.rho.dtype == torch.float64
+    x = torch.tensor(g["x_f64"], device=DEV)
+    out = m(x)
+    loss = _loss_head(out, torch.tensor([2], device=DEV))
+    loss.backward()
+    assert rel_l2(out.detach().cpu().numpy(), g["out_f64"]) < 1e-9
+    assert abs(loss.item() - float(g["loss_f64"])) < 1e-11
+    assert rel_l2(m.cell.geom.rho.grad.cpu().numpy(), g["rho_grad_f64"]) < 1e-8
+    g4 = load_golden("vowel_both")
+    m4 = _vowel_model(0.1, 1.0, -30.0)
+    x4 = torch.tensor(g4["x_f64"], device=DEV)
+    out4 = m4(x4)
+    _loss_head(out4, torch.arange(6, device=DEV) % 3).backward()
+    assert rel_l2(out4.detach().cpu().numpy(), g4["out_f64"]) < 1e-8
+    assert rel_l2(m4.cell.geom.rho.grad.cpu().numpy(), g4["rho_grad_f64"]) < 1e-7
+    # float32 product path vs the float64 GPU run of the same model
+    wt.utils.set_dtype("float32")
+    m32 = _vowel_model(0.1, 1.0, -30.0)
+    out32 = m32(x4.float())
+    assert rel_l2(out32.detach().cpu().numpy(), out4.detach().cpu().numpy()) < max(1e-5, 3 * rel_l2(g4["out_f32"], g4["out_f64"]))

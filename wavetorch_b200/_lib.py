@@ -21,7 +21,8 @@ WT_PATH_RESIDENT = 1
 
 EXPORTS = ("wt_abi_version", "wt_last_error", "wt_query_plan", "wt_validate_pixels", "wt_forward", "wt_backward", "wt_step_forward",
            "wt_step_backward", "wt_geom_forward", "wt_geom_backward", "wt_loss_forward", "wt_loss_backward",
-           "wt_peer_allreduce", "wt_slab_forward", "wt_slab_backward", "wt_slab_exchange")
+           "wt_peer_allreduce", "wt_slab_forward", "wt_slab_backward", "wt_slab_exchange", "wt_query_plan_f64", "wt_forward_f64",
+           "wt_backward_f64")
 
 
 class WtProblem(ctypes.Structure):
@@ -78,7 +79,11 @@ def load():
         lib.wt_slab_forward.argtypes = [ctypes.POINTER(WtProblem), vp] + [vp] * 11 + [vp, sz, vp, sz, vp]
         lib.wt_slab_backward.argtypes = [ctypes.POINTER(WtProblem), vp] + [vp] * 8 + [vp, sz] + [vp] * 4 + [vp, sz, vp]
         lib.wt_slab_exchange.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
-        for name in ("wt_slab_forward", "wt_slab_backward", "wt_slab_exchange"):
+        lib.wt_query_plan_f64.argtypes = [ctypes.POINTER(WtProblem), ctypes.POINTER(WtPlan)]
+        lib.wt_forward_f64.argtypes = [ctypes.POINTER(WtProblem)] + [vp] * 12 + [vp, sz, vp, sz, vp]
+        lib.wt_backward_f64.argtypes = [ctypes.POINTER(WtProblem)] + [vp] * 8 + [vp, sz] + [vp] * 4 + [vp, sz, vp]
+        for name in ("wt_slab_forward", "wt_slab_backward", "wt_slab_exchange", "wt_query_plan_f64", "wt_forward_f64",
+                     "wt_backward_f64"):
             getattr(lib, name).restype = ctypes.c_int
         for name in ("wt_query_plan", "wt_validate_pixels", "wt_forward", "wt_backward", "wt_step_forward", "wt_step_backward",
                      "wt_geom_forward", "wt_geom_backward", "wt_loss_forward", "wt_loss_backward",

@@ -15,7 +15,8 @@ _warned_f64 = False
 
 
 def _f32(t, name):
-    """The kernels compute in float32 (BASELINE north star); float64 inputs are cast with one warning."""
+    """float32 view of an input of the float32 paths (a float64 model takes _WaveLoop64 instead; what still arrives here in
+    float64 -- e.g. through TimeStep.apply -- is cast with one warning)."""
     global _warned_f64
     if t is None:
         return None
@@ -301,9 +302,92 @@ class _WaveLoop(torch.autograd.Function):
                 grad_b.to(bd) if need[2] else None, grad_rho.to(rd) if need[3] else None, None)
 
 
+class _WaveLoop64(torch.autograd.Function):
+    """The time loop in float64 (the reference's utils.set_dtype('float64') mode, utils.py:14-20): wt_forward_f64 /
+    wt_backward_f64, one launch per step on the streaming kernels.  Taken when x or the geometry is float64; no
+    checkpointing and no dLoss/dfields in this mode (the float32 paths are the product, this one is for double-precision
+    runs and cross-checks)."""
+
+    @staticmethod
+    def forward(ctx, x, c, b, rho, spec):
+        lib = _lib.load()
+        _require_cuda(x, "the input waveform x")
+        _require_cuda(c, "the wave speed c")
+        dev = x.device
+        f64 = lambda t: None if t is None else t.detach().to(torch.float64).contiguous()
+        x64, c64, b64, rho64 = f64(x), f64(c), f64(b), f64(rho)
+        B, T = x64.shape
+        Nx, Ny = c64.shape
+        need = ctx.needs_input_grad
+        nonlinear = spec.b0 > 0 or spec.c_nl != 0
+        want_grad = spec.track_grad and T > 0 and (need[0] or need[1] or need[2] or (need[3] and nonlinear))
+        if spec.output_fields and want_grad:
+            raise NotImplementedError("wavetorch_b200: gradients through output_fields=True are not available in float64; "
+                                      "use float32 or the probe outputs")
+        n_src, n_prb = spec.src_ij.shape[0], spec.prb_ij.shape[0]
+        prob = _lib.make_problem(Nx, Ny, B, T, n_src, n_prb, spec.dt, spec.h, spec.b0, spec.uth, spec.c_nl,
+                                 spec.flags | _lib.WT_F_ZERO_INIT, _dev_index(dev))
+        fe = max(int(spec.field_every), 1) if spec.output_fields else 1
+        prob.field_every = fe
+        plan = _lib.WtPlan()
+        _lib.check(lib.wt_query_plan_f64(ctypes.byref(prob), ctypes.byref(plan)), "wt_query_plan_f64")
+        u1 = torch.empty((B, Nx, Ny), device=dev, dtype=torch.float64)
+        u2 = torch.empty_like(u1)
+        probe_out = torch.empty((B, T, n_prb), device=dev, dtype=torch.float64)
+        probe_raw = torch.empty_like(probe_out) if want_grad else None
+        fields = torch.empty((B, T // fe, Nx, Ny), device=dev, dtype=torch.float64) if spec.output_fields else None
+        hist = torch.empty(max(int(plan.history_bytes), 16), device=dev, dtype=torch.uint8) if want_grad else None
+        ws = torch.empty(max(int(plan.workspace_fwd_bytes), 16), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            st = lib.wt_forward_f64(ctypes.byref(prob), _lib.ptr(c64), _lib.ptr(b64), _lib.ptr(rho64), _lib.ptr(x64),
+                                    _lib.ptr(spec.src_ij), _lib.ptr(spec.prb_ij), _lib.ptr(spec.prb_sq), _lib.ptr(u1),
+                                    _lib.ptr(u2), _lib.ptr(probe_out), _lib.ptr(probe_raw), _lib.ptr(fields), _lib.ptr(hist),
+                                    hist.numel() if hist is not None else 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(st, "wt_forward_f64")
+        _lib.count_launches(plan.launches_fwd)
+        ctx.no_tape = not want_grad
+        ctx.shape = (Nx, Ny)
+        if want_grad:
+            ctx.prob, ctx.plan, ctx.spec = prob, plan, spec
+            ctx.save_for_backward(c64, b64, rho64, probe_raw, hist)
+            ctx.dtypes = (x.dtype, c.dtype, b.dtype, rho.dtype if rho is not None else None)
+        return (fields if spec.output_fields else probe_out).to(x.dtype if x.dtype == torch.float64 else c.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if ctx.no_tape:
+            need = ctx.needs_input_grad
+            zero = torch.zeros(ctx.shape, device=grad_out.device, dtype=grad_out.dtype) if need[3] else None
+            return None, None, None, zero, None
+        lib = _lib.load()
+        prob, plan, spec = ctx.prob, ctx.plan, ctx.spec
+        c64, b64, rho64, probe_raw, hist = ctx.saved_tensors
+        dev = c64.device
+        B, T, Nx, Ny = prob.B, prob.T, prob.Nx, prob.Ny
+        need = ctx.needs_input_grad
+        g = grad_out.detach().to(torch.float64).contiguous()
+        grad_c = torch.empty((Nx, Ny), device=dev, dtype=torch.float64)
+        grad_b = torch.empty((Nx, Ny), device=dev, dtype=torch.float64) if need[2] else None
+        grad_rho = torch.empty((Nx, Ny), device=dev, dtype=torch.float64) if need[3] else None
+        grad_x = torch.empty((B, T), device=dev, dtype=torch.float64) if need[0] else None
+        ws = torch.empty(max(int(plan.workspace_bwd_bytes), 16), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            st = lib.wt_backward_f64(ctypes.byref(prob), _lib.ptr(c64), _lib.ptr(b64), _lib.ptr(rho64), _lib.ptr(spec.src_ij),
+                                     _lib.ptr(spec.prb_ij), _lib.ptr(spec.prb_sq), _lib.ptr(g), _lib.ptr(probe_raw),
+                                     _lib.ptr(hist), hist.numel(), _lib.ptr(grad_c), _lib.ptr(grad_b), _lib.ptr(grad_rho),
+                                     _lib.ptr(grad_x), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(st, "wt_backward_f64")
+        _lib.count_launches(plan.launches_bwd)
+        xd, cd, bd, rd = ctx.dtypes
+        return (grad_x.to(xd) if need[0] else None, grad_c.to(cd) if need[1] else None,
+                grad_b.to(bd) if need[2] else None, grad_rho.to(rd) if need[3] else None, None)
+
+
 def wave_rnn(x, c, b, rho, spec):
     """Run the fused time loop.  x [B,T]; c, b, rho [Nx,Ny]; returns [B,T,n_prb] (or [B,T,Nx,Ny])."""
     spec.track_grad = torch.is_grad_enabled()
+    if x.dtype == torch.float64 or c.dtype == torch.float64:
+        return _WaveLoop64.apply(x, c, b, rho, spec)
     T = x.shape[1]
     chunked = bool(spec.batch_chunk) and 0 < spec.batch_chunk < x.shape[0]
     if spec.checkpoint_every and 0 < spec.checkpoint_every < T and not chunked and not spec.output_fields and c.is_cuda:
