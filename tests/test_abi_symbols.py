@@ -12,7 +12,7 @@ from conftest import ROOT
 def _declared_functions():
     text = open(os.path.join(ROOT, "include", "wavetorch_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(wt_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(wt_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_declares_expected_entry_points():
