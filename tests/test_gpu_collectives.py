@@ -4,7 +4,6 @@ ghost-row exchange of the slab decomposition -- exercised on ONE GPU: the "ranks
 exactly as they do across GPUs (tests/test_multi_gpu.py repeats them over real peers when the box has >= 2 GPUs)."""
 import ctypes
 
-import numpy as np
 import pytest
 import torch
 

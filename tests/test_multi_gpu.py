@@ -3,7 +3,6 @@ Skipped on boxes with fewer than 2 GPUs; tests/test_gpu_collectives.py runs the 
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 
