@@ -110,12 +110,15 @@ class _CheckpointedLoop(torch.autograd.Function):
         chunks = [(b0, min(b0 + bc, B)) for b0 in range(0, B, bc)]
         out = torch.empty((B, T, n_prb), device=dev, dtype=torch.float32)
         ckpts = {}
+        # One chunk: its checkpoints are taken now.  Several chunks: keeping every chunk's checkpoints until the backward would
+        # defeat the chunking, so the backward re-runs a chunk's forward to take them (one more forward sweep).
+        keep_ck = want_grad and len(chunks) == 1
         for ci, (b0, b1) in enumerate(chunks):
             nb = b1 - b0
             u1 = torch.empty((nb, Nx, Ny), device=dev, dtype=torch.float32)
             u2 = torch.empty_like(u1)
             for k, (s0, s1) in enumerate(segs):
-                if k > 0 and want_grad:
+                if k > 0 and keep_ck:
                     ckpts[(ci, k)] = (u1.clone(), u2.clone())
                 prob = _CheckpointedLoop._problem(spec, Nx, Ny, nb, s1 - s0, dev, k == 0, False)
                 plan = _lib.query_plan(prob)
@@ -159,6 +162,18 @@ class _CheckpointedLoop(torch.autograd.Function):
         grad_x = torch.zeros((B, T), device=dev, dtype=torch.float32) if need[0] else None
         for ci, (b0, b1) in enumerate(chunks):
             nb = b1 - b0
+            if len(chunks) > 1 and len(segs) > 1:   # this chunk's checkpoints: its forward once more, without tape or outputs
+                u1 = torch.empty((nb, Nx, Ny), device=dev, dtype=torch.float32)
+                u2 = torch.empty_like(u1)
+                for k, (s0, s1) in enumerate(segs[:-1]):
+                    prob = _CheckpointedLoop._problem(spec, Nx, Ny, nb, s1 - s0, dev, k == 0, False)
+                    plan = _lib.query_plan(prob)
+                    ws = torch.empty(max(int(plan.workspace_fwd_bytes), 16), device=dev, dtype=torch.uint8)
+                    _call_forward(lib, prob, dev, c32, b32, rho32, x32[b0:b1, s0:s1].contiguous(), spec, u1, u2, None, None,
+                                  None, None, ws)
+                    _lib.count_launches(plan.launches_fwd)
+                    ckpts[(ci, k + 1)] = (u1.clone(), u2.clone())
+                del u1, u2
             adj1 = torch.zeros((nb, Nx, Ny), device=dev, dtype=torch.float32)
             adj2 = torch.zeros_like(adj1)
             for k in range(len(segs) - 1, -1, -1):
