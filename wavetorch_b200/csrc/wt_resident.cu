@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(pitch, li + 1, pj) : -1;
   }
+  L.pub_all = L.active && probe_in_interior<R>(a, L.rank, tid);
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
   const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;

@@ -128,6 +128,7 @@ template <int R>
 struct Lane {
   int rank, cid, tid, run, g, j0, lr0, gi0, slab;
   bool active;
+  bool pub_all;              // publish the interior cells of my patch too (a probe lane reads one of them from the slab buffer)
   bool edge_up, edge_dn;     // my patch borders the slab of rank-1 / rank+1
   bool arm_up, arm_dn;       // I re-arm the corresponding mbarrier
   uint32_t push_up, push_dn; // cluster address of the neighbour's ghost row slot (buffer 0)
@@ -144,6 +145,7 @@ struct Lane {
     cid = blockIdx.x / a.C;
     tid = threadIdx.x;
     active = tid < a.nact;
+    pub_all = false;
     run = tid / a.P4;
     g = tid - run * a.P4;
     j0 = 4 * g;
@@ -177,12 +179,15 @@ struct Lane {
   // Write my R rows into slab buffer `which` (0/1) and push the rim rows to the neighbours.
   // pitch: a.pitch, or the same value as a compile-time constant in the shape-specialised kernels
   __device__ __forceinline__ void publish(int pitch, float* fld, int which, const float (&v)[R][4]) {
+    // Only the RIM of my patch is ever read by another thread (rows 0 and R-1 by the patches above / below, columns 0 and 3
+    // by the ones left / right); the 2(R-2) interior cells stay in registers unless a probe lane needs one of them.
     const int PS = pitch >> 2;
     float* buf = fld + which * slab + (lr0 + 1) * pitch + g;
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) buf[r * pitch + k * PS] = v[r][k];
+      for (int k = 0; k < 4; ++k)
+        if (r == 0 || r == R - 1 || k == 0 || k == 3 || pub_all) buf[r * pitch + k * PS] = v[r][k];
     const uint32_t boff = (uint32_t)(which * slab) * 4u;
     const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
     if (edge_up) {
@@ -208,6 +213,20 @@ struct Lane {
     }
   }
 };
+
+// Does a probe sit on an interior cell of my patch?  (forward kernels: probe lanes sample the slab buffer)
+template <int R>
+__device__ __forceinline__ bool probe_in_interior(const ResArgs& a, int rank, int tid) {
+  if (R <= 2) return false;
+  for (int p = 0; p < a.n_prb; ++p) {
+    const int li = a.prb_ij[2 * p] - rank * a.Hc, pj = a.prb_ij[2 * p + 1];
+    if (li >= 0 && li < a.Hc && (li / R) * a.P4 + pj / 4 == tid) {
+      const int r = li % R, k = pj & 3;
+      if (r != 0 && r != R - 1 && k != 0 && k != 3) return true;
+    }
+  }
+  return false;
+}
 
 // Which of my 4R cells are sources?  m1 / m2: listed at least once / twice (rnn.py:56-57 adds x once per listing).
 // More than two listings of one pixel are not supported by this path (a third mask in the step body costs the common case

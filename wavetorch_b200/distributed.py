@@ -37,9 +37,12 @@ class _SumGradAcrossRanks(torch.autograd.Function):
     def backward(ctx, *grads):
         live = [g for g in grads if g is not None]
         if live:
-            flat = torch.cat([g.reshape(-1).to(torch.float32) for g in live]) if len(live) > 1 else \
-                live[0].reshape(-1).to(torch.float32).contiguous()
-            if ctx.reducer is not None and flat.is_cuda and flat.numel() <= ctx.reducer.capacity:
+            # float32 (the product path) goes through the peer-memory kernel; a float64 model (set_dtype('float64')) keeps its
+            # precision and takes the NCCL all-reduce
+            dt = torch.float64 if any(g.dtype == torch.float64 for g in live) else torch.float32
+            flat = torch.cat([g.reshape(-1).to(dt) for g in live]) if len(live) > 1 else \
+                live[0].reshape(-1).to(dt).contiguous()
+            if ctx.reducer is not None and flat.is_cuda and dt == torch.float32 and flat.numel() <= ctx.reducer.capacity:
                 flat = ctx.reducer.all_reduce(flat, ctx.scale)       # one kernel over NVLink peer memory (csrc/wt_peer.cu)
             else:
                 if live[0].reshape(-1).data_ptr() == flat.data_ptr():
