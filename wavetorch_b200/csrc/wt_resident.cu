@@ -42,10 +42,10 @@ template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false, boo
 __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
   const int pitch = PITCH ? PITCH : a.pitch;
-  const int slab_f = (a.Hc + 2) * pitch;
+  const int slab_f = slab_words(R, a.Hc, pitch);
   float* fld = reinterpret_cast<float*>(smem4);       // [2][slab]
   float* xs = fld + 2 * slab_f;                        // [2][TB]
-  float* ps = xs + 2 * TB;                             // [2][TB][n_prb]
+  float* ps = xs + 2 * TB;                             // [n_prb][2*TB]: a ring of 2*TB samples per probe
   int* poff = reinterpret_cast<int*>(ps + 2 * TB * a.n_prb);  // [n_prb] offset into a slab buffer, or -1
   uint64_t* bars = reinterpret_cast<uint64_t*>(poff + a.n_prb + (a.n_prb & 1));
 
@@ -58,13 +58,13 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
-    poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(pitch, li + 1, pj) : -1;
+    poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(R, pitch, li, pj) : -1;
   }
   L.pub_all = L.active && probe_in_interior<R>(a, L.rank, tid);
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
   const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
-  const int own = (L.lr0 + 1) * pitch + L.g;       // my first row inside a slab buffer
+  const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;       // my first row inside a slab buffer
   const size_t tape_step = (size_t)a.C * R * NT;        // float4 per time step of one sample
   const size_t plane = (size_t)a.Nx * a.Ny;
 
@@ -102,11 +102,11 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 
     auto flush = [&](int blk) {   // probe samples of time block blk -> HBM
       const int t0 = blk * TB, n = min(TB, a.T - t0);
-      const float* src = ps + (blk & 1) * TB * a.n_prb;
+      const float* src = ps + (blk & 1) * TB;
       for (int i = tid; i < n * a.n_prb; i += NT) {
         int p = i % a.n_prb;
         if (poff[p] >= 0) {
-          float val = src[i];
+          float val = src[p * (2 * TB) + i / a.n_prb];
           size_t o = ((size_t)b * Tst + toff + t0 + i / a.n_prb) * a.n_prb + p;
           if (a.probe_raw) a.probe_raw[o] = val;
           if (a.probe_out) a.probe_out[o] = a.prb_sq[p] ? val * val : val;
@@ -118,13 +118,14 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
     // is loop invariant.  x and the probe samples live in rings of 2*TB steps.
     const float* rd0 = fld + own;                 // my patch in slab buffer 0 / 1
     const float* rd1 = fld + L.slab + own;
-    float* psw = ps + tid;                        // probe ring slot of this lane (lanes < n_prb only)
+    float* psw = ps + tid * (2 * TB);             // sample ring of this lane's probe (lanes < n_prb only)
     auto step = [&](auto par, float (&cu)[R][4], float (&pr)[R][4], int t) {
       constexpr int PAR = decltype(par)::value;
       const float* cur = PAR ? rd1 : rd0;
       L.acquire_ghosts();
-      if (my_poff >= 0 && t > 0) psw[((t - 1) & (2 * TB - 1)) * a.n_prb] = (PAR ? fld + L.slab : fld)[my_poff];
+      if (my_poff >= 0 && t > 0) psw[(t - 1) & (2 * TB - 1)] = (PAR ? fld + L.slab : fld)[my_poff];
       if (L.active) {
+        const float xv = m1 ? xs[t & (2 * TB - 1)] : 0.f;   // fetched ahead of the stencil: off the source warp's path
         float lap[R][4];
         patch_laplacian<R>(pitch, cur, cu, lap);
 #pragma unroll
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
         if (m1) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t]
-          patch_inject<R>(pr, m1, m2, 0u, xs[t & (2 * TB - 1)]);
+          patch_inject_sw<R>(pr, m1, m2, xv);
         }
         L.publish(pitch, fld, PAR ^ 1, pr);
         if (TAPE) {
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
       }
     }
     L.acquire_ghosts();   // consume the last publish so that no st.async is in flight past this point
-    if (my_poff >= 0) ps[(((a.T - 1) / TB) & 1) * TB * a.n_prb + ((a.T - 1) % TB) * a.n_prb + tid] = fld[(a.T & 1) * L.slab + my_poff];
+    if (my_poff >= 0) psw[(a.T - 1) & (2 * TB - 1)] = fld[(a.T & 1) * L.slab + my_poff];
     __syncthreads();
     for (int blk = max(0, nblk - 2); blk < nblk; ++blk) flush(blk);
     // final state back to HBM: u1 = latest field, u2 = the one before (cell.py:107)
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   const int RG = RINGC ? RINGC : a.ring;
   const int RG_LOG = RINGC ? (RINGC == 2 ? 1 : RINGC == 4 ? 2 : RINGC == 8 ? 3 : 4) : (31 - __clz(a.ring));
   const int pitch = PITCH ? PITCH : a.pitch;
-  const int slab_f = (a.Hc + 2) * pitch;
+  const int slab_f = slab_words(R, a.Hc, pitch);
   const unsigned stage_bytes = (unsigned)(R * NT * sizeof(float4));
 
   extern __shared__ float4 smem4[];
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     if (pown[p] == tid) {
       if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
     }
-  const int own = (L.lr0 + 1) * pitch + L.g;
+  const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;
   const size_t tape_step = (size_t)a.C * R * NT;
   // the lane that re-issues tape copies sits in a middle warp: the first and last warps already wait for ghost rows
   const int refill_tid = ((NT / 32) / 2) * 32;
@@ -488,11 +489,11 @@ __global__ void k_finish_grad_p(const float* __restrict__ G, const float* __rest
 // =================================================================================================
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-static size_t smem_fwd_bytes(int Hc, int pitch, int n_prb) {
-  return (size_t)2 * (Hc + 2) * pitch * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)(n_prb + 1) * 4 + 4 * 8 + 16;
+static size_t smem_fwd_bytes(int Hc, int pitch, int n_prb, int R) {
+  return (size_t)2 * slab_words(R, Hc, pitch) * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)(n_prb + 1) * 4 + 4 * 8 + 16;
 }
 static size_t smem_adj_bytes(int Hc, int pitch, int n_prb, int R, int threads, int ring) {
-  return (size_t)ring * R * threads * 16 + (size_t)2 * (Hc + 2) * pitch * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
+  return (size_t)ring * R * threads * 16 + (size_t)2 * slab_words(R, Hc, pitch) * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
          (size_t)2 * n_prb * 4 + 8 + MAX_RING * 8 + 4 * 8 + 16;
 }
 
@@ -625,17 +626,17 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
       if (nl) {
         if (!ring_for(Hc, R, threads)) continue;
       } else {
-        if (need_adjoint ? !ring_lin(Hc, R, threads) : (int)smem_fwd_bytes(Hc, pitch, p->n_prb) > smem_cap) continue;
+        if (need_adjoint ? !ring_lin(Hc, R, threads) : (int)smem_fwd_bytes(Hc, pitch, p->n_prb, R) > smem_cap) continue;
       }
       // estimated time per step ~ (waves of clusters) x (rows per CTA) / (per-thread efficiency)
       size_t sf, sb;
       int ncl;
       if (nl) {
-        sf = res_nl_smem_fwd(Hc, pitch, p->n_prb);
+        sf = res_nl_smem_fwd(Hc, pitch, p->n_prb, R);
         sb = res_nl_smem_adj(Hc, pitch, p->n_prb, R, threads, ring_for(Hc, R, threads));
         ncl = res_nl_clusters_cached(p->device, R, nl, C, threads, sf, sb);
       } else {
-        sf = smem_fwd_bytes(Hc, pitch, p->n_prb);
+        sf = smem_fwd_bytes(Hc, pitch, p->n_prb, R);
         sb = smem_adj_bytes(Hc, pitch, p->n_prb, R, threads, ring_lin(Hc, R, threads));
         ncl = resident_clusters(p->device, R, C, threads, sf, sb);
       }
@@ -678,13 +679,13 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
   if (nl) {
     const int ring = ring_for(Hc, bestR, threads);
     plan->reserved[0] = ring;
-    plan->smem_fwd = (int)res_nl_smem_fwd(Hc, pitch, p->n_prb);
+    plan->smem_fwd = (int)res_nl_smem_fwd(Hc, pitch, p->n_prb, bestR);
     plan->smem_bwd = (int)res_nl_smem_adj(Hc, pitch, p->n_prb, bestR, threads, ring);
     ncl = res_nl_clusters_cached(p->device, bestR, nl, bestC, threads, plan->smem_fwd, plan->smem_bwd);
   } else {
     const int ring = ring_lin(Hc, bestR, threads);
     plan->reserved[0] = ring;
-    plan->smem_fwd = (int)smem_fwd_bytes(Hc, pitch, p->n_prb);
+    plan->smem_fwd = (int)smem_fwd_bytes(Hc, pitch, p->n_prb, bestR);
     plan->smem_bwd = (int)smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads, ring);
     ncl = resident_clusters(p->device, bestR, bestC, threads, plan->smem_fwd, plan->smem_bwd);
   }

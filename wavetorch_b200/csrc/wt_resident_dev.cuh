@@ -108,13 +108,32 @@ __device__ __forceinline__ void st_async_b32(uint32_t remote_addr, float x, uint
 // with consecutive lanes on consecutive words -- one wavefront -- including the left / right rim (plane 3 at g-1, plane 0
 // at g+1; for the first / last thread those are the zero pads, i.e. the zero boundary).  With the row-major layout the rim
 // loads were 32-bit loads 16 bytes apart, a 4-way bank conflict each, and made up 60 % of the kernel's wavefronts.
-__device__ __forceinline__ int slab_cell(int pitch, int row, int col) { return row * pitch + (col & 3) * (pitch >> 2) + (col >> 2); }
+//
+// Run skew: a warp's 32 lanes usually straddle two runs (a run = the P4 threads that share R rows; P4 = 25 at Ny = 100 is
+// not a multiple of 32).  The lanes of the second run sit R*pitch words further on, and with R*pitch = 520 = 8 (mod 32) they
+// land on banks the first run's lanes already use: EVERY access of such a warp was a 2-way conflict (ncu: 909 shared-memory
+// wavefronts per CTA and step where the instruction count says 480).  Shifting the rows of run k by k*skew words with
+// R*pitch + skew = P4 (mod 32) makes the bank of a lane tid + const (mod 32): one wavefront per access for every warp.
+__host__ __device__ constexpr int slab_skew(int R, int pitch) { return ((pitch >> 2) - 1 - R * pitch) & 31; }
+// words of one slab buffer: Hc + 2 rows (one ghost row per side) plus the skew of runs -1 .. Hc/R
+__host__ __device__ constexpr int slab_words(int R, int Hc, int pitch) { return (Hc + 2) * pitch + (Hc / R + 1) * slab_skew(R, pitch); }
+// offset of local row li (-1 = ghost row above, Hc = ghost row below) inside a slab buffer
+__host__ __device__ constexpr int slab_row(int R, int pitch, int li) {
+  return (li + 1) * pitch + (li < 0 ? 0 : li / R + 1) * slab_skew(R, pitch);
+}
+__host__ __device__ constexpr int slab_cell(int R, int pitch, int li, int col) {
+  return slab_row(R, pitch, li) + (col & 3) * (pitch >> 2) + (col >> 2);
+}
+// Wait for ghost rows pushed by st.async from a neighbour CTA.  The data arrives through the async proxy and is counted on
+// MY mbarrier (complete_tx): observing the phase with the default CTA-scope acquire orders it before my shared-memory
+// reads -- the same pattern a TMA-multicast consumer uses.  An .acquire.cluster wait is not needed and makes ptxas emit a
+// CCTL.IVALL (L1 invalidate) after every successful wait, on the edge warps' critical path.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WT_WAITC:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra WT_DONEC;\n"
       "bra WT_WAITC;\n"
       "WT_DONEC:\n"
@@ -151,7 +170,7 @@ struct Lane {
     j0 = 4 * g;
     lr0 = run * R;
     gi0 = rank * a.Hc + lr0;
-    slab = (a.Hc + 2) * a.pitch;
+    slab = slab_words(R, a.Hc, a.pitch);
     gbar = bars;
     row_bytes = (unsigned)a.P4 * 16u;
     npub = 0;
@@ -161,7 +180,7 @@ struct Lane {
     arm_dn = edge_dn && j0 == 0;
     push_up = push_dn = rbar_up = rbar_dn = 0;
     if (edge_up) {   // my top row is the ghost row BELOW the last row of rank-1
-      push_up = mapa_u32(smem_u32(fld + (a.Hc + 1) * a.pitch + g), rank - 1);
+      push_up = mapa_u32(smem_u32(fld + slab_row(R, a.pitch, a.Hc) + g), rank - 1);
       rbar_up = mapa_u32(smem_u32(bars + 2), rank - 1);
     }
     if (edge_dn) {   // my bottom row is the ghost row ABOVE the first row of rank+1
@@ -182,7 +201,7 @@ struct Lane {
     // Only the RIM of my patch is ever read by another thread (rows 0 and R-1 by the patches above / below, columns 0 and 3
     // by the ones left / right); the 2(R-2) interior cells stay in registers unless a probe lane needs one of them.
     const int PS = pitch >> 2;
-    float* buf = fld + which * slab + (lr0 + 1) * pitch + g;
+    float* buf = fld + which * slab + (lr0 + 1) * pitch + (run + 1) * slab_skew(R, pitch) + g;
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -266,12 +285,12 @@ __device__ __forceinline__ void load_coef(const ResArgs& a, bool active, int gi0
 template <int R>
 __device__ __forceinline__ void patch_laplacian(int pitch, const float* own, const float (&v)[R][4], float (&lap)[R][4]) {
   // `own` points at plane 0 of my first row inside the slab buffer (slab_cell layout)
-  const int PS = pitch >> 2;
+  const int PS = pitch >> 2, SK = slab_skew(R, pitch);   // the rows above / below belong to the neighbouring runs
   float upv[4], dnv[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    upv[k] = own[k * PS - pitch];
-    dnv[k] = own[k * PS + R * pitch];
+    upv[k] = own[k * PS - pitch - SK];
+    dnv[k] = own[k * PS + R * pitch + SK];
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -296,7 +315,7 @@ constexpr int res_max_threads() {
 
 // host entry points of wt_resident_nl.cu
 int res_nl_max_threads_rt(int R);
-size_t res_nl_smem_fwd(int Hc, int pitch, int n_prb);
+size_t res_nl_smem_fwd(int Hc, int pitch, int n_prb, int R);
 size_t res_nl_smem_adj(int Hc, int pitch, int n_prb, int R, int threads, int ring);
 int res_nl_clusters(int R, int nl, int C, int threads, size_t smem_fwd, size_t smem_bwd);
 int res_nl_launch_fwd(const wt_plan& plan, const ResArgs& a, cudaStream_t st, bool ckpt = false);

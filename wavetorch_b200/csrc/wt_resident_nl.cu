@@ -59,7 +59,7 @@ template <int R, bool SAT, bool KERR, bool FIELDS = false, int PITCH = 0, int NT
 __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd_nl(ResArgs a) {
   extern __shared__ float4 smem4[];
   const int pitch = PITCH ? PITCH : a.pitch;
-  const int slab_f = (a.Hc + 2) * pitch;
+  const int slab_f = slab_words(R, a.Hc, pitch);
   float* fld = reinterpret_cast<float*>(smem4);
   float* xs = fld + 2 * slab_f;
   float* ps = xs + 2 * TB;
@@ -87,13 +87,13 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
   source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
-    poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(pitch, li + 1, pj) : -1;
+    poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(R, pitch, li, pj) : -1;
   }
   L.pub_all = L.active && probe_in_interior<R>(a, L.rank, tid);
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
   const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
-  const int own = (L.lr0 + 1) * pitch + L.g;
+  const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;
   const size_t tape_step = (size_t)a.C * 2 * R * NT;
   const size_t plane = (size_t)a.Nx * a.Ny;
   const Scalars s = a.s;
@@ -132,11 +132,11 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
 
     auto flush = [&](int blk) {
       const int t0 = blk * TB, n = min(TB, a.T - t0);
-      const float* src = ps + (blk & 1) * TB * a.n_prb;
+      const float* src = ps + (blk & 1) * TB;      // ps: [n_prb][2*TB], a ring of 2*TB samples per probe
       for (int i = tid; i < n * a.n_prb; i += NT) {
         int p = i % a.n_prb;
         if (poff[p] >= 0) {
-          float val = src[i];
+          float val = src[p * (2 * TB) + i / a.n_prb];
           size_t o = ((size_t)b * Tst + toff + t0 + i / a.n_prb) * a.n_prb + p;
           if (a.probe_raw) a.probe_raw[o] = val;
           if (a.probe_out) a.probe_out[o] = a.prb_sq[p] ? val * val : val;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
     auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int t, int blk, int tt) {
       const float* cur = fld + (t & 1) * L.slab;
       L.acquire_ghosts();
-      if (t > 0 && my_poff >= 0) ps[(((t - 1) / TB) & 1) * TB * a.n_prb + ((t - 1) % TB) * a.n_prb + tid] = cur[my_poff];
+      if (t > 0 && my_poff >= 0) ps[tid * (2 * TB) + ((t - 1) & (2 * TB - 1))] = cur[my_poff];
       if (L.active) {
         float lap[R][4];
         patch_laplacian<R>(pitch, cur + own, cu, lap);
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
             }
             pr[r][k] = wt_update(q + q, q * kc2, u, pr[r][k], lap[r][k]);
           }
-        if (m1) patch_inject<R>(pr, m1, m2, 0u, xs[(blk & 1) * TB + tt]);
+        if (m1) patch_inject_sw<R>(pr, m1, m2, xs[(blk & 1) * TB + tt]);
         L.publish(pitch, fld, (t + 1) & 1, pr);
         if (FIELDS && (t + 1) % a.field_every == 0) {
 #pragma unroll
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
       }
     }
     L.acquire_ghosts();
-    if (my_poff >= 0) ps[(((a.T - 1) / TB) & 1) * TB * a.n_prb + ((a.T - 1) % TB) * a.n_prb + tid] = fld[(a.T & 1) * L.slab + my_poff];
+    if (my_poff >= 0) ps[tid * (2 * TB) + ((a.T - 1) & (2 * TB - 1))] = fld[(a.T & 1) * L.slab + my_poff];
     __syncthreads();
     for (int blk = max(0, nblk - 2); blk < nblk; ++blk) flush(blk);
 #pragma unroll
@@ -257,7 +257,7 @@ template <int R, bool SAT, bool KERR, int PITCH = 0, int NTC = 0, int GRADX = 1,
 __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj_nl(ResArgs a) {
   const int NT = NTC ? NTC : blockDim.x;
   const int pitch = PITCH ? PITCH : a.pitch;
-  const int slab_f = (a.Hc + 2) * pitch;
+  const int slab_f = slab_words(R, a.Hc, pitch);
   const int RG = a.ring;                        // 2 or 4 (resident_plan)
   const unsigned rg_mask = (unsigned)RG - 1u, rg_shift = RG == 4 ? 2u : 1u;
   const int stage_f4 = 2 * R * NT;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
     if (pown[p] == tid) {
       if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
     }
-  const int own = (L.lr0 + 1) * pitch + L.g;
+  const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;
   const Scalars s = a.s;
   const float ndtb0 = -s.dt * s.b0, two_iu2 = 2.f * s.inv_uth * s.inv_uth;
 
@@ -514,11 +514,11 @@ int res_nl_max_threads_rt(int R) {
   }
 }
 
-size_t res_nl_smem_fwd(int Hc, int pitch, int n_prb) {
-  return (size_t)2 * (Hc + 2) * pitch * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)(n_prb + 1) * 4 + 4 * 8 + 16;
+size_t res_nl_smem_fwd(int Hc, int pitch, int n_prb, int R) {
+  return (size_t)2 * slab_words(R, Hc, pitch) * 4 + 2 * TB * 4 + (size_t)2 * TB * n_prb * 4 + (size_t)(n_prb + 1) * 4 + 4 * 8 + 16;
 }
 size_t res_nl_smem_adj(int Hc, int pitch, int n_prb, int R, int threads, int ring) {
-  return (size_t)ring * 2 * R * threads * 16 + (size_t)2 * (Hc + 2) * pitch * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
+  return (size_t)ring * 2 * R * threads * 16 + (size_t)2 * slab_words(R, Hc, pitch) * 4 + (size_t)2 * TB * n_prb * 4 + 2 * TB * 4 +
          (size_t)2 * n_prb * 4 + 8 + RING * 8 + 4 * 8 + 16;
 }
 
