@@ -142,27 +142,29 @@ __device__ __forceinline__ void patch_inject(float (&P)[R][4], unsigned m1, unsi
   }
 }
 
-// P[cell] += v through a switch over the 4R registers: ptxas turns it into a short compare tree plus jump tables, ~10
-// instructions on the owning warp's path where the row-wise select above costs a branch region per row.  Used by the
-// on-chip kernels, whose step is paced by the slowest warp of the CTA.
-template <int R>
-__device__ __forceinline__ void patch_add_switch(float (&P)[R][4], int cell, float v) {
-#define WT_CASE(i) case i: if (i < 4 * R) P[(i) / 4 < R ? (i) / 4 : 0][(i) % 4] += v; break;
-  switch (cell) {
-    WT_CASE(0) WT_CASE(1) WT_CASE(2) WT_CASE(3) WT_CASE(4) WT_CASE(5) WT_CASE(6) WT_CASE(7)
-    WT_CASE(8) WT_CASE(9) WT_CASE(10) WT_CASE(11) WT_CASE(12) WT_CASE(13) WT_CASE(14) WT_CASE(15)
-    WT_CASE(16) WT_CASE(17) WT_CASE(18) WT_CASE(19) WT_CASE(20) WT_CASE(21) WT_CASE(22) WT_CASE(23)
-    WT_CASE(24) WT_CASE(25) WT_CASE(26) WT_CASE(27) WT_CASE(28) WT_CASE(29) WT_CASE(30) WT_CASE(31)
-    default: break;
-  }
-#undef WT_CASE
+// P += x at the cells listed in m (bit r*4+k = cell (r,k)) as 4R predicated adds without a branch.  For the on-chip kernels,
+// whose step is paced by the slowest warp of the CTA: the caller tests "does any lane of my warp own a source" (warp-uniform)
+// and only that warp issues these ~2*4R instructions; the row-wise select of patch_inject costs it a divergent branch
+// region per row, a switch over the cell index (tried) a compare tree with 13-cycle predicate-to-branch latencies.
+// inline PTX: written as C++ the 4R bit tests are loop invariant and nvcc keeps 4R extracted bits in registers
+template <int BIT>
+__device__ __forceinline__ void add_if_bit(float& p, unsigned m, float x) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 t;\n"
+      "and.b32 t, %1, %2;\n"
+      "setp.ne.b32 p, t, 0;\n"
+      "@p add.f32 %0, %0, %3;\n"
+      "}\n"
+      : "+f"(p)
+      : "r"(m), "n"(1u << BIT), "f"(x));
 }
-// P += x at the cells listed in m1, once more at those also in m2 (source.py:19-22 adds x once per listing, in sequence)
-template <int R>
-__device__ __forceinline__ void patch_inject_sw(float (&P)[R][4], unsigned m1, unsigned m2, float x) {
-  for (unsigned mm = m1; mm; mm &= mm - 1u) {
-    const int bit = __ffs(mm) - 1;
-    for (int n = (m2 >> bit & 1u) ? 2 : 1; n; --n) patch_add_switch<R>(P, bit, x);
+template <int R, int I = 0>
+__device__ __forceinline__ void patch_inject_pred(float (&P)[R][4], unsigned m, float x) {
+  if constexpr (I < 4 * R) {
+    add_if_bit<I>(P[I / 4][I % 4], m, x);
+    patch_inject_pred<R, I + 1>(P, m, x);
   }
 }
 

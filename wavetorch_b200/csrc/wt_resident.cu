@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
   unsigned m1, m2;
   source_masks<R>(a, L.active, L.gi0, L.j0, m1, m2);
+  const bool src_warp = __any_sync(0xffffffffu, m1 != 0u), src2_warp = __any_sync(0xffffffffu, m2 != 0u);
   for (int p = tid; p < a.n_prb; p += NT) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(R, pitch, li, pj) : -1;
@@ -125,15 +126,16 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
       L.acquire_ghosts();
       if (my_poff >= 0 && t > 0) psw[(t - 1) & (2 * TB - 1)] = (PAR ? fld + L.slab : fld)[my_poff];
       if (L.active) {
-        const float xv = m1 ? xs[t & (2 * TB - 1)] : 0.f;   // fetched ahead of the stencil: off the source warp's path
+        const float xv = src_warp ? xs[t & (2 * TB - 1)] : 0.f;   // fetched ahead of the stencil: off the source warp's path
         float lap[R][4];
         patch_laplacian<R>(pitch, cur, cu, lap);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
-        if (m1) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t]
-          patch_inject_sw<R>(pr, m1, m2, xv);
+        if (src_warp) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t], once per listing
+          patch_inject_pred<R>(pr, m1, xv);
+          if (src2_warp) patch_inject_pred<R>(pr, m2, xv);
         }
         L.publish(pitch, fld, PAR ^ 1, pr);
         if (TAPE) {

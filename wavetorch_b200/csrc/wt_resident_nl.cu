@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
             }
             pr[r][k] = wt_update(q + q, q * kc2, u, pr[r][k], lap[r][k]);
           }
-        if (m1) patch_inject_sw<R>(pr, m1, m2, xs[(blk & 1) * TB + tt]);
+        if (m1) patch_inject<R>(pr, m1, m2, 0u, xs[(blk & 1) * TB + tt]);
         L.publish(pitch, fld, (t + 1) & 1, pr);
         if (FIELDS && (t + 1) % a.field_every == 0) {
 #pragma unroll
