@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
   const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
+  // a warp without special duties: all lanes own cells, none borders another CTA, owns a source, samples a probe or has to
+  // publish interior cells for a probe lane; and the FIELDS / CKPT instantiations keep to the general step
+  const bool plain_warp = !FIELDS && !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || L.pub_all || m1 != 0u || my_poff >= 0);
   const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;       // my first row inside a slab buffer
   const size_t tape_step = (size_t)a.C * R * NT;        // float4 per time step of one sample
   const size_t plane = (size_t)a.Nx * a.Ny;
@@ -120,24 +123,32 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
     const float* rd0 = fld + own;                 // my patch in slab buffer 0 / 1
     const float* rd1 = fld + L.slab + own;
     float* psw = ps + tid * (2 * TB);             // sample ring of this lane's probe (lanes < n_prb only)
-    auto step = [&](auto par, float (&cu)[R][4], float (&pr)[R][4], int t) {
+    // PLAIN: the instantiation for warps without special duties (plain_warp below) carries none of the flag tests and
+    // branch regions of the general step -- ghost-row waits and pushes, probe sampling, source injection, inactive lanes.
+    // Those cost a warp ~30 instructions and six divergence regions per step even when every one of them is skipped, and
+    // the step is paced by the sum of what the three warps of a scheduler issue.
+    auto step = [&](auto par, auto plain_t, float (&cu)[R][4], float (&pr)[R][4], int t) {
       constexpr int PAR = decltype(par)::value;
+      constexpr bool PLAIN = decltype(plain_t)::value;
       const float* cur = PAR ? rd1 : rd0;
-      L.acquire_ghosts();
-      if (my_poff >= 0 && t > 0) psw[(t - 1) & (2 * TB - 1)] = (PAR ? fld + L.slab : fld)[my_poff];
-      if (L.active) {
-        const float xv = src_warp ? xs[t & (2 * TB - 1)] : 0.f;   // fetched ahead of the stencil: off the source warp's path
+      if (!PLAIN) {
+        L.acquire_ghosts();
+        if (my_poff >= 0 && t > 0) psw[(t - 1) & (2 * TB - 1)] = (PAR ? fld + L.slab : fld)[my_poff];
+      }
+      if (PLAIN || L.active) {
+        float xv = 0.f;
+        if (!PLAIN) xv = src_warp ? xs[t & (2 * TB - 1)] : 0.f;   // fetched ahead of the stencil: off the source warp's path
         float lap[R][4];
         patch_laplacian<R>(pitch, cur, cu, lap);
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
           for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
-        if (src_warp) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t], once per listing
+        if (!PLAIN && src_warp) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t], once per listing
           patch_inject_pred<R>(pr, m1, xv);
           if (src2_warp) patch_inject_pred<R>(pr, m2, xv);
         }
-        L.publish(pitch, fld, PAR ^ 1, pr);
+        L.template publish<PLAIN>(pitch, fld, PAR ^ 1, pr);
         if (TAPE) {
 #pragma unroll
           for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
@@ -160,42 +171,48 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
           fout += plane;
         }
       }
-      ++L.npub;
+      if (!PLAIN) ++L.npub;
       __syncthreads();
     };
     using P0 = std::integral_constant<int, 0>;
     using P1 = std::integral_constant<int, 1>;
 
     const int nblk = (a.T + TB - 1) / TB;
-    for (int blk = 0; blk < nblk; ++blk) {
-      const int t0 = blk * TB, n = min(TB, a.T - t0);
-      if ((blk + 1) * TB < a.T) {   // stage the next block of x
-        float* dst = xs + ((blk + 1) & 1) * TB;
-        const int t1 = (blk + 1) * TB;
-        for (int i = tid; i < TB && t1 + i < a.T; i += NT) dst[i] = xb[t1 + i];
-      }
-      if (blk >= 2) flush(blk - 2);
-      if (CKPT && a.snap_every && t0 > 0 && (toff + t0) % a.snap_every == 0) {   // v = u_{t-1}, w = u_{t-2}: blocks are even
-        float4* sp = a.snap + ((((size_t)((toff + t0) / a.snap_every - 1) * a.B + b) * a.C + L.rank) * 2 * R) * NT + tid;
+    const unsigned npub0 = L.npub;
+    auto run = [&](auto plain_t) {
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int t0 = blk * TB, n = min(TB, a.T - t0);
+        if ((blk + 1) * TB < a.T) {   // stage the next block of x
+          float* dst = xs + ((blk + 1) & 1) * TB;
+          const int t1 = (blk + 1) * TB;
+          for (int i = tid; i < TB && t1 + i < a.T; i += NT) dst[i] = xb[t1 + i];
+        }
+        if (blk >= 2) flush(blk - 2);
+        if (CKPT && a.snap_every && t0 > 0 && (toff + t0) % a.snap_every == 0) {   // v = u_{t-1}, w = u_{t-2}: blocks are even
+          float4* sp = a.snap + ((((size_t)((toff + t0) / a.snap_every - 1) * a.B + b) * a.C + L.rank) * 2 * R) * NT + tid;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          sp[r * NT] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-          sp[(R + r) * NT] = make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
+          for (int r = 0; r < R; ++r) {
+            sp[r * NT] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+            sp[(R + r) * NT] = make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
+          }
+        }
+        int tt = 0;
+        for (; tt + 1 < n; tt += 2) {     // two steps per iteration: the two time levels swap roles, no moves
+          step(P0{}, plain_t, v, w, t0 + tt);
+          step(P1{}, plain_t, w, v, t0 + tt + 1);
+        }
+        if (tt < n) {                      // odd tail (last block only): keep "v = latest" by swapping once
+          step(P0{}, plain_t, v, w, t0 + tt);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { float tmp = v[r][k]; v[r][k] = w[r][k]; w[r][k] = tmp; }
         }
       }
-      int tt = 0;
-      for (; tt + 1 < n; tt += 2) {     // two steps per iteration: the two time levels swap roles, no moves
-        step(P0{}, v, w, t0 + tt);
-        step(P1{}, w, v, t0 + tt + 1);
-      }
-      if (tt < n) {                      // odd tail (last block only): keep "v = latest" by swapping once
-        step(P0{}, v, w, t0 + tt);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { float tmp = v[r][k]; v[r][k] = w[r][k]; w[r][k] = tmp; }
-      }
-    }
+    };
+    // Every warp executes the same sequence of __syncthreads(); only the instruction stream between them differs.
+    if (plain_warp) run(std::true_type{}); else run(std::false_type{});
+    L.npub = npub0 + (unsigned)a.T;
     L.acquire_ghosts();   // consume the last publish so that no st.async is in flight past this point
     if (my_poff >= 0) psw[(a.T - 1) & (2 * TB - 1)] = fld[(a.T & 1) * L.slab + my_poff];
     __syncthreads();

@@ -196,6 +196,9 @@ struct Lane {
 
   // Write my R rows into slab buffer `which` (0/1) and push the rim rows to the neighbours.
   // pitch: a.pitch, or the same value as a compile-time constant in the shape-specialised kernels
+  // PLAIN: the caller knows that no lane of this warp borders another CTA or must publish interior cells (see the kernels'
+  // plain_warp): the rim stores only, no flag tests and no branch regions
+  template <bool PLAIN = false>
   __device__ __forceinline__ void publish(int pitch, float* fld, int which, const float (&v)[R][4]) {
     // Only the RIM of my patch is ever read by another thread (rows 0 and R-1 by the patches above / below, columns 0 and 3
     // by the ones left / right); the 2(R-2) interior cells stay in registers unless a probe lane needs one of them.
@@ -205,7 +208,8 @@ struct Lane {
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (r == 0 || r == R - 1 || k == 0 || k == 3 || pub_all) buf[r * pitch + k * PS] = v[r][k];
+        if (r == 0 || r == R - 1 || k == 0 || k == 3 || (!PLAIN && pub_all)) buf[r * pitch + k * PS] = v[r][k];
+    if (PLAIN) return;
     const uint32_t boff = (uint32_t)(which * slab) * 4u;
     const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
     if (edge_up) {
