@@ -61,10 +61,11 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(R, pitch, li, pj) : -1;
   }
-  L.pub_all = L.active && probe_in_interior<R>(a, L.rank, tid);
+  L.pub_all = L.active && probe_in_interior<R>(a, L.rank, L.lt);
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
-  const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
+  const int plane_lane = NT - 1 - tid;   // probe p is sampled by lane NT-1-p: the highest warp has issue priority
+  const int my_poff = (plane_lane < a.n_prb) ? poff[plane_lane] : -1;
   // a warp without special duties: all lanes own cells, none borders another CTA, owns a source, samples a probe or has to
   // publish interior cells for a probe lane; and the FIELDS / CKPT instantiations keep to the general step
   const bool plain_warp = !FIELDS && !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || L.pub_all || m1 != 0u || my_poff >= 0);
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
     // is loop invariant.  x and the probe samples live in rings of 2*TB steps.
     const float* rd0 = fld + own;                 // my patch in slab buffer 0 / 1
     const float* rd1 = fld + L.slab + own;
-    float* psw = ps + tid * (2 * TB);             // sample ring of this lane's probe (lanes < n_prb only)
+    float* psw = ps + plane_lane * (2 * TB);      // sample ring of this lane's probe (the last n_prb lanes only)
     // PLAIN: the instantiation for warps without special duties (plain_warp below) carries none of the flag tests and
     // branch regions of the general step -- ghost-row waits and pushes, probe sampling, source injection, inactive lanes.
     // Those cost a warp ~30 instructions and six divergence regions per step even when every one of them is skipped, and
@@ -293,13 +294,15 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
   int pc0 = -1, pi0 = 0;       // first probe inside my patch: cell index and probe index
   bool more_probes = false;
   for (int p = 0; p < a.n_prb; ++p)
-    if (pown[p] == tid) {
+    if (pown[p] == L.lt) {
       if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
     }
   const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;
   const size_t tape_step = (size_t)a.C * R * NT;
   // the lane that re-issues tape copies sits in a middle warp: the first and last warps already wait for ghost rows
   const int refill_tid = ((NT / 32) / 2) * 32;
+  const bool plain_warp = !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || pc0 >= 0 || tid == refill_tid ||
+                                                       (GRADX && a.grad_x && m1 != 0u));
 
   float G[R][4];
 #pragma unroll
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
         patch_fma_cell<R>(P, k3, pc0, srow[pi0]);
         if (more_probes) {
           for (int p = pi0 + 1; p < a.n_prb; ++p)
-            if (pown[p] == tid) patch_fma_cell<R>(P, k3, pcell[p], srow[p]);
+            if (pown[p] == L.lt) patch_fma_cell<R>(P, k3, pcell[p], srow[p]);
         }
       }
     };
@@ -382,12 +385,15 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
     const float* rd0 = fld + own;
     const float* rd1 = fld + L.slab + own;
     const float4* ring_me = ring + tid;
-    auto step = [&](auto par, float (&cu)[R][4], float (&pr)[R][4], int t, int it) {
+    // PLAIN: instantiation for warps without special duties (plain_warp), as in k_res_fwd: no ghost-row wait or push, no
+    // probe seeds, no dLoss/dx gather, no tape refill, all lanes active
+    auto step = [&](auto par, auto plain_t, float (&cu)[R][4], float (&pr)[R][4], int t, int it) {
       constexpr int PAR = decltype(par)::value;
+      constexpr bool PLAIN = decltype(plain_t)::value;
       const float* cur = PAR ? rd1 : rd0;
       const unsigned gi = it_global + it;
       const unsigned slot = gi & (RG - 1), parity = (gi >> RG_LOG) & 1u;
-      L.acquire_ghosts();
+      if (!PLAIN) L.acquire_ghosts();
       // EARLY (small patches): the stencil update and the ghost-row push come first, the tape stage and the gradient
       // accumulation -- which need neither the ghost rows nor the new field -- after.  With a handful of rows per CTA the
       // step time is the ring  push -> DSMEM flight -> neighbour's wait -> its update -> its push;  everything an edge
@@ -402,14 +408,14 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
           if (!CHAIN || t > 0) {
-            add_seeds(pr, t - 1);
-            L.publish(pitch, fld, PAR ^ 1, pr);
+            if (!PLAIN) add_seeds(pr, t - 1);
+            L.template publish<PLAIN>(pitch, fld, PAR ^ 1, pr);
           }
         }
       };
-      if (EARLY && L.active) stencil();
-      if (L.active) {
-        if (GRADX && a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
+      if (EARLY && (PLAIN || L.active)) stencil();
+      if (PLAIN || L.active) {
+        if (!PLAIN && GRADX && a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
           // a loop over the (few) source cells of this thread with one division each: 4R unrolled divisions would
           // triple the size of the step body for code that one thread per sample executes
           float s = 0.f;
@@ -439,30 +445,36 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
         }
         if (!EARLY) stencil();
       }
-      if (t > 0) ++L.npub;
+      if (!PLAIN && t > 0) ++L.npub;
       __syncthreads();
-      if (tid == refill_tid && it + RG < a.T) {   // every thread has read this slot: refill it RG steps ahead
+      if (!PLAIN && tid == refill_tid && it + RG < a.T) {   // every thread has read this slot: refill it RG steps ahead
         mbar_expect_tx(full + slot, stage_bytes);
         bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(t - RG) * tape_step, stage_bytes, full + slot);
       }
     };
     using P0 = std::integral_constant<int, 0>;
     using P1 = std::integral_constant<int, 1>;
-    int t = a.T - 1, it = 0;
-    for (; t >= 1; t -= 2, it += 2) {
-      // Staging bookkeeping, once per block of TB steps and outside the step bodies (their code size is what the
-      // instruction cache sees 2T times per sample).  When a block starts at the second step of the pair its seeds are
-      // staged one step early: the half they go to held the seeds of the block before the previous one, all consumed.
-      const int tb = ((t & (TB - 1)) == TB - 1) ? t : ((((t - 1) & (TB - 1)) == TB - 1) ? t - 1 : -1);
-      if (tb >= 0 && tb != a.T - 1 && tb >= TB) stage_seeds(tb / TB - 1);
-      step(P0{}, v, w, t, it);
-      step(P1{}, w, v, t - 1, it + 1);
-      if (GRADX && a.grad_x) {   // dLoss/dx of a block goes out right after its last (lowest) step
-        if ((t & (TB - 1)) == 0 && t >= TB) flush_gx(t / TB);
-        if (((t - 1) & (TB - 1)) == 0 && t - 1 >= TB) flush_gx((t - 1) / TB);
+    const unsigned npub0 = L.npub;
+    auto run = [&](auto plain_t) {
+      int t = a.T - 1, it = 0;
+      for (; t >= 1; t -= 2, it += 2) {
+        // Staging bookkeeping, once per block of TB steps and outside the step bodies (their code size is what the
+        // instruction cache sees 2T times per sample).  When a block starts at the second step of the pair its seeds are
+        // staged one step early: the half they go to held the seeds of the block before the previous one, all consumed.
+        const int tb = ((t & (TB - 1)) == TB - 1) ? t : ((((t - 1) & (TB - 1)) == TB - 1) ? t - 1 : -1);
+        if (tb >= 0 && tb != a.T - 1 && tb >= TB) stage_seeds(tb / TB - 1);
+        step(P0{}, plain_t, v, w, t, it);
+        step(P1{}, plain_t, w, v, t - 1, it + 1);
+        if (GRADX && a.grad_x) {   // dLoss/dx of a block goes out right after its last (lowest) step
+          if ((t & (TB - 1)) == 0 && t >= TB) flush_gx(t / TB);
+          if (((t - 1) & (TB - 1)) == 0 && t - 1 >= TB) flush_gx((t - 1) / TB);
+        }
       }
-    }
-    if (t == 0) step(P0{}, v, w, 0, it);
+      if (t == 0) step(P0{}, plain_t, v, w, 0, it);
+    };
+    // every warp executes the same sequence of __syncthreads(); only the instruction stream between them differs
+    if (plain_warp) run(std::true_type{}); else run(std::false_type{});
+    L.npub = npub0 + (unsigned)(a.T - 1);
     it_global += (unsigned)a.T;
     if (CHAIN && a.chain_out) {   // (P_{-1}, P_0): after an even number of steps they sit in (v, w), else in (w, v)
       float4* cp = a.chain + ((size_t)b * a.C + L.rank) * 2 * R * NT + tid;

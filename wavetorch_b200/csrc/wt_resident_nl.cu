@@ -89,10 +89,11 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
     int li = a.prb_ij[2 * p] - L.rank * a.Hc, pj = a.prb_ij[2 * p + 1];
     poff[p] = (li >= 0 && li < a.Hc) ? slab_cell(R, pitch, li, pj) : -1;
   }
-  L.pub_all = L.active && probe_in_interior<R>(a, L.rank, tid);
+  L.pub_all = L.active && probe_in_interior<R>(a, L.rank, L.lt);
   for (int i = tid; i < 2 * slab_f; i += NT) fld[i] = 0.f;
   if (a.C > 1) cg::this_cluster().sync(); else __syncthreads();
-  const int my_poff = (tid < a.n_prb) ? poff[tid] : -1;
+  const int plane_lane = NT - 1 - tid;   // probe p is sampled by lane NT-1-p: the highest warp has issue priority
+  const int my_poff = (plane_lane < a.n_prb) ? poff[plane_lane] : -1;
   const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;
   const size_t tape_step = (size_t)a.C * 2 * R * NT;
   const size_t plane = (size_t)a.Nx * a.Ny;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
     auto step = [&](float (&cu)[R][4], float (&pr)[R][4], int t, int blk, int tt) {
       const float* cur = fld + (t & 1) * L.slab;
       L.acquire_ghosts();
-      if (t > 0 && my_poff >= 0) ps[tid * (2 * TB) + ((t - 1) & (2 * TB - 1))] = cur[my_poff];
+      if (t > 0 && my_poff >= 0) ps[plane_lane * (2 * TB) + ((t - 1) & (2 * TB - 1))] = cur[my_poff];
       if (L.active) {
         float lap[R][4];
         patch_laplacian<R>(pitch, cur + own, cu, lap);
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_fwd
       }
     }
     L.acquire_ghosts();
-    if (my_poff >= 0) ps[tid * (2 * TB) + ((a.T - 1) & (2 * TB - 1))] = fld[(a.T & 1) * L.slab + my_poff];
+    if (my_poff >= 0) ps[plane_lane * (2 * TB) + ((a.T - 1) & (2 * TB - 1))] = fld[(a.T & 1) * L.slab + my_poff];
     __syncthreads();
     for (int blk = max(0, nblk - 2); blk < nblk; ++blk) flush(blk);
 #pragma unroll
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
   int pc0 = -1, pi0 = 0;
   bool more_probes = false;
   for (int p = 0; p < a.n_prb; ++p)
-    if (pown[p] == tid) {
+    if (pown[p] == L.lt) {
       if (pc0 < 0) { pc0 = pcell[p]; pi0 = p; } else more_probes = true;
     }
   const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_nl_max_threads<R>()) k_res_adj
           patch_add_cell<R>(lam, pc0, srow[pi0]);
           if (more_probes) {
             for (int p = pi0 + 1; p < a.n_prb; ++p)
-              if (pown[p] == tid) patch_add_cell<R>(lam, pcell[p], srow[p]);
+              if (pown[p] == L.lt) patch_add_cell<R>(lam, pcell[p], srow[p]);
           }
         }
         if (GRADX && a.grad_x && m1) {
