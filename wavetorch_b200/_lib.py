@@ -9,7 +9,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwavetorch_b200.so")
+LIB_PATH = os.environ.get("WT_LIB") or os.path.join(_HERE, "lib", "libwavetorch_b200.so")   # WT_LIB: a debug build
 
 WT_F_ZERO_INIT = 1
 WT_F_FORCE_STREAM = 2

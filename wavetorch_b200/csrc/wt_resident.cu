@@ -39,7 +39,7 @@ namespace wt {
 // start from a stored snapshot of the register patches and stores snapshots every snap_every steps (a multiple of TB) on
 // its way; the common kernels carry none of that code.
 template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false, bool CKPT = false>
-__global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
+__global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_blocks<R>(NTC)) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
   const int pitch = PITCH ? PITCH : a.pitch;
   const int slab_f = slab_words(R, a.Hc, pitch);
@@ -132,29 +132,50 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
       constexpr int PAR = decltype(par)::value;
       constexpr bool PLAIN = decltype(plain_t)::value;
       const float* cur = PAR ? rd1 : rd0;
+#ifdef WT_DEBUG_CLOCK
+      long long c0 = clock64(), c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+#endif
       if (!PLAIN) {
         L.acquire_ghosts();
+#ifdef WT_DEBUG_CLOCK
+        c1 = clock64();
+#endif
         if (my_poff >= 0 && t > 0) psw[(t - 1) & (2 * TB - 1)] = (PAR ? fld + L.slab : fld)[my_poff];
       }
+#ifdef WT_DEBUG_CLOCK
+      c2 = clock64();
+#endif
       if (PLAIN || L.active) {
         float xv = 0.f;
         if (!PLAIN) xv = src_warp ? xs[t & (2 * TB - 1)] : 0.f;   // fetched ahead of the stencil: off the source warp's path
         float lap[R][4];
         patch_laplacian<R>(pitch, cur, cu, lap);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
-        if (!PLAIN && src_warp) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t], once per listing
-          patch_inject_pred<R>(pr, m1, xv);
-          if (src2_warp) patch_inject_pred<R>(pr, m2, xv);
-        }
-        L.template publish<PLAIN>(pitch, fld, PAR ^ 1, pr);
         if (TAPE) {
+          // The tape rows go out BEFORE the update and the publish.  The LSU queue is in order: issued last, the 128-bit
+          // tape stores of the warps that finish early sit in front of the rim stores and ghost-row pushes of the warps
+          // that finish late -- the ones the step barrier waits for (measured: 700-1200 cycles for an edge warp's publish).
 #pragma unroll
           for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
           tape += tape_step;
         }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
+#ifdef WT_DEBUG_CLOCK
+        c3 = clock64();
+#endif
+        if (!PLAIN && src_warp) {   // source.py:19-22 (dt = 1.0 there): every listed pixel receives x[b,t], once per listing
+          patch_inject_pred<R>(pr, m1, xv);
+          if (src2_warp) patch_inject_pred<R>(pr, m2, xv);
+        }
+#ifdef WT_DEBUG_CLOCK
+        c4 = clock64();
+#endif
+        L.template publish<PLAIN>(pitch, fld, PAR ^ 1, pr);
+#ifdef WT_DEBUG_CLOCK
+        c5 = clock64();
+#endif
         if (FIELDS && (t + 1) % a.field_every == 0) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -173,6 +194,10 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
         }
       }
       if (!PLAIN) ++L.npub;
+#ifdef WT_DEBUG_CLOCK
+      if ((tid & 31) == 0 && (int)blockIdx.x < 2 && b == (int)blockIdx.x / a.C && (t == 500 || t == 503))
+        printf("F cta=%d t=%d w=%d plain=%d arrive=%lld acq=%lld prb=%lld upd=%lld inj=%lld pub=%lld end=%lld\n", (int)blockIdx.x, t, tid >> 5, (int)PLAIN, clock64(), c1 - c0, c2 - c0, c3 - c0, c4 - c0, c5 - c0, clock64() - c0);
+#endif
       __syncthreads();
     };
     using P0 = std::integral_constant<int, 0>;
@@ -252,7 +277,7 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_fwd(ResArgs a) {
 // of longer sequences; the pair (P_{t-1}, P_t) at the segment boundary is handed from launch to launch through a.chain
 // in the register layout (no lambda <-> P conversion, no division), and the per-cluster gradient partials accumulate.
 template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1, int RINGC = 0, bool CHAIN = false>
-__global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
+__global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_blocks<R>(NTC)) k_res_adj(ResArgs a) {
   constexpr bool EARLY = R <= 2;   // see the step body
   const int NT = NTC ? NTC : blockDim.x;
   const int RG = RINGC ? RINGC : a.ring;
@@ -446,6 +471,10 @@ __global__ void __launch_bounds__(res_max_threads<R>()) k_res_adj(ResArgs a) {
         if (!EARLY) stencil();
       }
       if (!PLAIN && t > 0) ++L.npub;
+#ifdef WT_DEBUG_CLOCK
+      if ((tid & 31) == 0 && (int)blockIdx.x < 2 && b == (int)blockIdx.x / a.C && t >= 500 && t < 504)
+        printf("A cta=%d t=%d w=%d plain=%d arrive=%lld\n", (int)blockIdx.x, t, tid >> 5, (int)PLAIN, clock64());
+#endif
       __syncthreads();
       if (!PLAIN && tid == refill_tid && it + RG < a.T) {   // every thread has read this slot: refill it RG steps ahead
         mbar_expect_tx(full + slot, stage_bytes);
@@ -584,14 +613,27 @@ static int active_clusters(K kernel, int C, int threads, size_t smem) {
   return n;
 }
 
+// Shape-specialised instantiations: (rows per thread, row pitch, threads per CTA, tape ring) as compile-time constants, so
+// that every shared-memory and tape offset of the step body is an immediate (5-14 % on the step).  One entry per plan the
+// planner picks for the grids and batch sizes of the reference's study configs; anything else runs the generic kernels
+// (bitwise the same results: tests/test_gpu_parity.py::test_shape_specialised_kernels_match_generic_ones).
+//   X(R, PITCH, THREADS, RING)
+#define WT_SPEC_SHAPES(X)                                                                                              \
+  X(5, 104, 384, 4)  /* 150x100, C=2: study/example.yml geometry at B >= 64 (BASELINE config 3, bench.py)          */ \
+  X(5, 104, 224, 4)  /* 150x100, C=4, two CTAs per SM (experiment)                                                */ \
+  X(2, 104, 256, 16) /* 150x100, C=8: example.yml at its own batch_size 6; config 3 sharded 8 per GPU             */ \
+  X(2, 144, 320, 8)  /* 140x140, C=8: study/linear/linear.yml (batch_size 9)                                      */ \
+  X(2, 156, 384, 8)  /* 151x151, C=8: study/propagate.py, study/optimize_lens.py (BASELINE configs 1-2)           */
+
 // Clusters that can be co-resident for both kernels of a decomposition (0 = cannot launch).  Cached per device.
-static int resident_clusters(int device, int R, int C, int threads, size_t smem_fwd, size_t smem_bwd) {
-  struct Key { int dev, R, C, threads; size_t sf, sb; int n; };
+static int resident_clusters(int device, int R, int C, int threads, size_t smem_fwd, size_t smem_bwd, int pitch, int ring,
+                             bool specialize) {
+  struct Key { int dev, R, C, threads; size_t sf, sb; int spec, n; };
   static std::mutex mu;
   static std::vector<Key> cache;
   std::lock_guard<std::mutex> lock(mu);
   for (const Key& k : cache)
-    if (k.dev == device && k.R == R && k.C == C && k.threads == threads && k.sf == smem_fwd && k.sb == smem_bwd) return k.n;
+    if (k.dev == device && k.R == R && k.C == C && k.threads == threads && k.sf == smem_fwd && k.sb == smem_bwd && k.spec == (int)specialize) return k.n;
   int nf = 0, nb = 0;
   switch (R) {
 #define WT_OCC(R_) case R_: { int n0 = active_clusters(k_res_fwd<R_, false>, C, threads, smem_fwd); int n1 = active_clusters(k_res_fwd<R_, true>, C, threads, smem_fwd); nf = n0 < n1 ? n0 : n1; nb = active_clusters(k_res_adj<R_>, C, threads, smem_bwd); } break;
@@ -599,8 +641,24 @@ static int resident_clusters(int device, int R, int C, int threads, size_t smem_
 #undef WT_OCC
     default: break;
   }
+  // a shape-specialised instantiation is what will be launched: its register budget (two CTAs per SM for the small ones) counts
+  if (specialize) {
+#define WT_SPEC_OCC(R_, P_, N_, G_)                                                                        \
+    if (R == R_ && pitch == P_ && threads == N_) {                                                           \
+      int n0 = active_clusters(k_res_fwd<R_, false, P_, N_>, C, threads, smem_fwd);                          \
+      int n1 = active_clusters(k_res_fwd<R_, true, P_, N_>, C, threads, smem_fwd);                           \
+      nf = n0 < n1 ? n0 : n1;                                                                                \
+      if (ring == G_) {                                                                                      \
+        int b0 = active_clusters(k_res_adj<R_, P_, N_, 0, G_>, C, threads, smem_bwd);                        \
+        int b1 = active_clusters(k_res_adj<R_, P_, N_, 1, G_>, C, threads, smem_bwd);                        \
+        nb = b0 < b1 ? b0 : b1;                                                                              \
+      }                                                                                                      \
+    }
+    WT_SPEC_SHAPES(WT_SPEC_OCC)
+#undef WT_SPEC_OCC
+  }
   int n = nf < nb ? nf : nb;
-  cache.push_back(Key{device, R, C, threads, smem_fwd, smem_bwd, n});
+  cache.push_back(Key{device, R, C, threads, smem_fwd, smem_bwd, (int)specialize, n});
   return n;
 }
 
@@ -669,7 +727,7 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
       } else {
         sf = smem_fwd_bytes(Hc, pitch, p->n_prb, R);
         sb = smem_adj_bytes(Hc, pitch, p->n_prb, R, threads, ring_lin(Hc, R, threads));
-        ncl = resident_clusters(p->device, R, C, threads, sf, sb);
+        ncl = resident_clusters(p->device, R, C, threads, sf, sb, pitch, ring_lin(Hc, R, threads), !(p->flags & WT_F_NO_SPECIALIZE));
       }
       if (ncl < 1) continue;
       const int waves = (p->B + ncl - 1) / ncl;
@@ -718,7 +776,7 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
     plan->reserved[0] = ring;
     plan->smem_fwd = (int)smem_fwd_bytes(Hc, pitch, p->n_prb, bestR);
     plan->smem_bwd = (int)smem_adj_bytes(Hc, pitch, p->n_prb, bestR, threads, ring);
-    ncl = resident_clusters(p->device, bestR, bestC, threads, plan->smem_fwd, plan->smem_bwd);
+    ncl = resident_clusters(p->device, bestR, bestC, threads, plan->smem_fwd, plan->smem_bwd, pitch, ring, !(p->flags & WT_F_NO_SPECIALIZE));
   }
   if (ncl < 1) return false;
   plan->n_clusters = p->B < ncl ? p->B : ncl;
@@ -769,17 +827,6 @@ static int launch_cluster(K kernel, const wt_plan& plan, size_t smem, const ResA
   WT_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
   return WT_OK;
 }
-
-// Shape-specialised instantiations: (rows per thread, row pitch, threads per CTA, tape ring) as compile-time constants, so
-// that every shared-memory and tape offset of the step body is an immediate (5-14 % on the step).  One entry per plan the
-// planner picks for the grids and batch sizes of the reference's study configs; anything else runs the generic kernels
-// (bitwise the same results: tests/test_gpu_parity.py::test_shape_specialised_kernels_match_generic_ones).
-//   X(R, PITCH, THREADS, RING)
-#define WT_SPEC_SHAPES(X)                                                                                              \
-  X(5, 104, 384, 4)  /* 150x100, C=2: study/example.yml geometry at B >= 64 (BASELINE config 3, bench.py)          */ \
-  X(2, 104, 256, 16) /* 150x100, C=8: example.yml at its own batch_size 6; config 3 sharded 8 per GPU             */ \
-  X(2, 144, 320, 8)  /* 140x140, C=8: study/linear/linear.yml (batch_size 9)                                      */ \
-  X(2, 156, 384, 8)  /* 151x151, C=8: study/propagate.py, study/optimize_lens.py (BASELINE configs 1-2)           */
 
 #define WT_DISPATCH_R(R_, CALL)                  \
   switch (R_) {                                  \

@@ -320,6 +320,10 @@ constexpr int res_max_threads() {
   return R <= 2 ? 512 : R == 3 ? 640 : R == 4 ? 512 : R == 5 ? 384 : R == 6 ? 320 : 256;
 }
 
+// Shape-specialised instantiations with few threads are compiled for two CTAs per SM (register budget 65536 / 2 / threads)
+template <int R>
+constexpr int res_min_blocks(int ntc) { return (R == 5 && ntc > 0 && ntc <= 224) ? 2 : 1; }
+
 // host entry points of wt_resident_nl.cu
 int res_nl_max_threads_rt(int R);
 size_t res_nl_smem_fwd(int Hc, int pitch, int n_prb, int R);
