@@ -41,6 +41,9 @@ namespace wt {
 template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false, bool CKPT = false>
 __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_blocks<R>(NTC)) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
+#ifdef WT_DEBUG_CLOCK
+  __shared__ long long wt_dbg[16][2][8];
+#endif
   const int pitch = PITCH ? PITCH : a.pitch;
   const int slab_f = slab_words(R, a.Hc, pitch);
   float* fld = reinterpret_cast<float*>(smem4);       // [2][slab]
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
         if (!PLAIN) xv = src_warp ? xs[t & (2 * TB - 1)] : 0.f;   // fetched ahead of the stencil: off the source warp's path
         float lap[R][4];
         patch_laplacian<R>(pitch, cur, cu, lap);
-        if (TAPE) {
+        if (TAPE && PLAIN) {
           // The tape rows go out BEFORE the update and the publish.  The LSU queue is in order: issued last, the 128-bit
           // tape stores of the warps that finish early sit in front of the rim stores and ghost-row pushes of the warps
           // that finish late -- the ones the step barrier waits for (measured: 700-1200 cycles for an edge warp's publish).
@@ -176,6 +179,11 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
 #ifdef WT_DEBUG_CLOCK
         c5 = clock64();
 #endif
+        if (TAPE && !PLAIN) {   // a warp with special duties: its rim stores and pushes are what others wait for, the tape comes last
+#pragma unroll
+          for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
+          tape += tape_step;
+        }
         if (FIELDS && (t + 1) % a.field_every == 0) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -195,8 +203,10 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
       }
       if (!PLAIN) ++L.npub;
 #ifdef WT_DEBUG_CLOCK
-      if ((tid & 31) == 0 && (int)blockIdx.x < 2 && b == (int)blockIdx.x / a.C && (t == 500 || t == 503))
-        printf("F cta=%d t=%d w=%d plain=%d arrive=%lld acq=%lld prb=%lld upd=%lld inj=%lld pub=%lld end=%lld\n", (int)blockIdx.x, t, tid >> 5, (int)PLAIN, clock64(), c1 - c0, c2 - c0, c3 - c0, c4 - c0, c5 - c0, clock64() - c0);
+      if ((tid & 31) == 0 && (int)blockIdx.x < 2 && b == (int)blockIdx.x / a.C && (t == 500 || t == 501)) {
+        long long* d = wt_dbg[tid >> 5][t - 500];
+        d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3; d[4] = c4; d[5] = c5; d[6] = clock64(); d[7] = PLAIN;
+      }
 #endif
       __syncthreads();
     };
@@ -257,6 +267,16 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
       }
     __syncthreads();
   }
+#ifdef WT_DEBUG_CLOCK
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < 2 && a.T > 502)
+    for (int w = 0; w < NT / 32; ++w)
+      for (int k = 0; k < 2; ++k) {
+        long long* d = wt_dbg[w][k];
+        printf("F cta=%d step=%d w=%d plain=%lld c0=%lld acq=%lld prb=%lld upd=%lld inj=%lld pub=%lld arrive=%lld\n", (int)blockIdx.x, k, w, d[7],
+               d[0] - wt_dbg[0][0][0], d[1] ? d[1] - d[0] : 0, d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0], d[6] - d[0]);
+      }
+#endif
   if (a.C > 1) cg::this_cluster().sync();   // nobody exits while a neighbour could still address its shared memory
 }
 
@@ -287,6 +307,9 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
   const unsigned stage_bytes = (unsigned)(R * NT * sizeof(float4));
 
   extern __shared__ float4 smem4[];
+#ifdef WT_DEBUG_CLOCK
+  __shared__ long long wt_dbg[16][2][8];
+#endif
   float4* ring = smem4;                                        // [RG][R*NT] tape stages
   float* fld = reinterpret_cast<float*>(ring + RG * R * NT);    // [2][slab]   P
   float* ss = fld + 2 * slab_f;                                 // [2][TB][n_prb] probe seeds
@@ -418,7 +441,13 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
       const float* cur = PAR ? rd1 : rd0;
       const unsigned gi = it_global + it;
       const unsigned slot = gi & (RG - 1), parity = (gi >> RG_LOG) & 1u;
+#ifdef WT_DEBUG_CLOCK
+      long long c0 = clock64(), c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+#endif
       if (!PLAIN) L.acquire_ghosts();
+#ifdef WT_DEBUG_CLOCK
+      c1 = clock64();
+#endif
       // EARLY (small patches): the stencil update and the ghost-row push come first, the tape stage and the gradient
       // accumulation -- which need neither the ghost rows nor the new field -- after.  With a handful of rows per CTA the
       // step time is the ring  push -> DSMEM flight -> neighbour's wait -> its update -> its push;  everything an edge
@@ -439,6 +468,9 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
         }
       };
       if (EARLY && (PLAIN || L.active)) stencil();
+#ifdef WT_DEBUG_CLOCK
+      c2 = clock64();
+#endif
       if (PLAIN || L.active) {
         if (!PLAIN && GRADX && a.grad_x && m1) {   // source.py:22: dLoss/dx[b,t] = sum over listed pixels of lambda_t = P_t / a3
           // a loop over the (few) source cells of this thread with one division each: 4R unrolled divisions would
@@ -459,6 +491,9 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
           atomicAdd(gxs + (t & (2 * TB - 1)), s);
         }
         mbar_wait(full + slot, parity);
+#ifdef WT_DEBUG_CLOCK
+        c3 = clock64();
+#endif
         const float4* rs = ring_me + slot * R * NT;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -468,12 +503,17 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
           G[r][2] = fmaf(l.z, cu[r][2], G[r][2]);
           G[r][3] = fmaf(l.w, cu[r][3], G[r][3]);
         }
+#ifdef WT_DEBUG_CLOCK
+        c4 = clock64();
+#endif
         if (!EARLY) stencil();
       }
       if (!PLAIN && t > 0) ++L.npub;
 #ifdef WT_DEBUG_CLOCK
-      if ((tid & 31) == 0 && (int)blockIdx.x < 2 && b == (int)blockIdx.x / a.C && t >= 500 && t < 504)
-        printf("A cta=%d t=%d w=%d plain=%d arrive=%lld\n", (int)blockIdx.x, t, tid >> 5, (int)PLAIN, clock64());
+      if ((tid & 31) == 0 && (int)blockIdx.x < 2 && b == (int)blockIdx.x / a.C && (t == 500 || t == 501)) {
+        long long* d = wt_dbg[tid >> 5][501 - t];
+        d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3; d[4] = c4; d[5] = 0; d[6] = clock64(); d[7] = PLAIN;
+      }
 #endif
       __syncthreads();
       if (!PLAIN && tid == refill_tid && it + RG < a.T) {   // every thread has read this slot: refill it RG steps ahead
@@ -531,6 +571,16 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
         *gp = (CHAIN && a.accumulate) ? *gp + G[r][k] : G[r][k];
       }
     }
+#ifdef WT_DEBUG_CLOCK
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < 2 && a.T > 502)
+    for (int w = 0; w < NT / 32; ++w)
+      for (int k = 0; k < 2; ++k) {
+        long long* d = wt_dbg[w][k];
+        printf("A cta=%d step=%d w=%d plain=%lld c0=%lld acq=%lld sten=%lld tapew=%lld G=%lld arrive=%lld\n", (int)blockIdx.x, k, w, d[7],
+               d[0] - wt_dbg[0][0][0], d[1] - d[0], d[2] - d[0], d[3] ? d[3] - d[0] : 0, d[4] ? d[4] - d[0] : 0, d[6] - d[0]);
+      }
+#endif
   if (a.C > 1) cg::this_cluster().sync();
 }
 
@@ -620,7 +670,6 @@ static int active_clusters(K kernel, int C, int threads, size_t smem) {
 //   X(R, PITCH, THREADS, RING)
 #define WT_SPEC_SHAPES(X)                                                                                              \
   X(5, 104, 384, 4)  /* 150x100, C=2: study/example.yml geometry at B >= 64 (BASELINE config 3, bench.py)          */ \
-  X(5, 104, 224, 4)  /* 150x100, C=4, two CTAs per SM (experiment)                                                */ \
   X(2, 104, 256, 16) /* 150x100, C=8: example.yml at its own batch_size 6; config 3 sharded 8 per GPU             */ \
   X(2, 144, 320, 8)  /* 140x140, C=8: study/linear/linear.yml (batch_size 9)                                      */ \
   X(2, 156, 384, 8)  /* 151x151, C=8: study/propagate.py, study/optimize_lens.py (BASELINE configs 1-2)           */

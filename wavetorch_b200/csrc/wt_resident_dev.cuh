@@ -207,23 +207,26 @@ struct Lane {
     // Only the RIM of my patch is ever read by another thread (rows 0 and R-1 by the patches above / below, columns 0 and 3
     // by the ones left / right); the 2(R-2) interior cells stay in registers unless a probe lane needs one of them.
     const int PS = pitch >> 2;
+    if (!PLAIN) {
+      // The pushes go first: the LSU queue is in order, and what the neighbour CTA's edge warp waits for should not sit
+      // behind my own rim stores (and whatever other warps have queued)
+      const uint32_t boff = (uint32_t)(which * slab) * 4u;
+      const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
+      if (edge_up) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st_async_b32(push_up + boff + (uint32_t)(k * PS) * 4u, v[0][k], rbar_up + bsel);
+      }
+      if (edge_dn) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st_async_b32(push_dn + boff + (uint32_t)(k * PS) * 4u, v[R - 1][k], rbar_dn + bsel);
+      }
+    }
     float* buf = fld + which * slab + (lr0 + 1) * pitch + (run + 1) * slab_skew(R, pitch) + g;
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (r == 0 || r == R - 1 || k == 0 || k == 3 || (!PLAIN && pub_all)) buf[r * pitch + k * PS] = v[r][k];
-    if (PLAIN) return;
-    const uint32_t boff = (uint32_t)(which * slab) * 4u;
-    const uint32_t bsel = (npub & 1u) * 8u;    // this is publish number npub: signal the barrier of its parity
-    if (edge_up) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) st_async_b32(push_up + boff + (uint32_t)(k * PS) * 4u, v[0][k], rbar_up + bsel);
-    }
-    if (edge_dn) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) st_async_b32(push_dn + boff + (uint32_t)(k * PS) * 4u, v[R - 1][k], rbar_dn + bsel);
-    }
   }
 
   // Wait until the neighbours' rows of the latest publish have landed in my ghost rows; re-arm for the next one.
@@ -320,9 +323,12 @@ constexpr int res_max_threads() {
   return R <= 2 ? 512 : R == 3 ? 640 : R == 4 ? 512 : R == 5 ? 384 : R == 6 ? 320 : 256;
 }
 
-// Shape-specialised instantiations with few threads are compiled for two CTAs per SM (register budget 65536 / 2 / threads)
+// Minimum CTAs per SM a shape-specialised instantiation is compiled for.  Two CTAs of 40 rows per SM (C = 4, R = 5, 224
+// threads, 144 registers) were measured against one of 75 rows (round 2): they do overlap (forward 0.77 us per step for
+// two against 0.54 for one alone) but a 40-row CTA carries too much fixed cost per step, and at 144 registers the adjoint
+// spills: forward with tape 0.81 = 0.81, adjoint 1.34 against 0.85.  Everything is built for one CTA per SM.
 template <int R>
-constexpr int res_min_blocks(int ntc) { return (R == 5 && ntc > 0 && ntc <= 224) ? 2 : 1; }
+constexpr int res_min_blocks(int) { return 1; }
 
 // host entry points of wt_resident_nl.cu
 int res_nl_max_threads_rt(int R);
