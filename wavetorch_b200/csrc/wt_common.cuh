@@ -168,4 +168,24 @@ __device__ __forceinline__ void patch_inject_pred(float (&P)[R][4], unsigned m, 
   }
 }
 
+// P[cell] += K[cell] * v as 4R compare-and-predicated-FMA pairs without a branch (cell < 0: nothing); see patch_inject_pred
+template <int I>
+__device__ __forceinline__ void fma_if_cell(float& p, float k, int cell, float v) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.eq.s32 p, %1, %2;\n"
+      "@p fma.rn.f32 %0, %3, %4, %0;\n"
+      "}\n"
+      : "+f"(p)
+      : "r"(cell), "n"(I), "f"(k), "f"(v));
+}
+template <int R, int I = 0>
+__device__ __forceinline__ void patch_fma_pred(float (&P)[R][4], const float (&K)[R][4], int cell, float v) {
+  if constexpr (I < 4 * R) {
+    fma_if_cell<I>(P[I / 4][I % 4], K[I / 4][I % 4], cell, v);
+    patch_fma_pred<R, I + 1>(P, K, cell, v);
+  }
+}
+
 }  // namespace wt

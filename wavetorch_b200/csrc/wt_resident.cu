@@ -143,7 +143,6 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
 #ifdef WT_DEBUG_CLOCK
         c1 = clock64();
 #endif
-        if (my_poff >= 0 && t > 0) psw[(t - 1) & (2 * TB - 1)] = (PAR ? fld + L.slab : fld)[my_poff];
       }
 #ifdef WT_DEBUG_CLOCK
       c2 = clock64();
@@ -201,7 +200,13 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
           fout += plane;
         }
       }
-      if (!PLAIN) ++L.npub;
+      if (!PLAIN) {
+        ++L.npub;
+        // The probe lanes sample the field of the previous step at the END of this step (its buffer is not written before
+        // the barrier): at the top the load would queue behind the stencil loads of the whole CTA and the dependent store
+        // would hold this warp back for ~400 cycles (measured with the WT_DEBUG_CLOCK build).
+        if (my_poff >= 0 && t > 0) psw[(t - 1) & (2 * TB - 1)] = (PAR ? fld + L.slab : fld)[my_poff];
+      }
 #ifdef WT_DEBUG_CLOCK
       if ((tid & 31) == 0 && (int)blockIdx.x < 2 && b == (int)blockIdx.x / a.C && (t == 500 || t == 501)) {
         long long* d = wt_dbg[tid >> 5][t - 500];
@@ -299,6 +304,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
 template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1, int RINGC = 0, bool CHAIN = false>
 __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_blocks<R>(NTC)) k_res_adj(ResArgs a) {
   constexpr bool EARLY = R <= 2;   // see the step body
+  constexpr bool SEED_PRED = R >= 4;   // big patches: probe seeds fetched ahead and added with predicated FMAs (R = 5: adjoint -3 %; slower at R = 2)
   const int NT = NTC ? NTC : blockDim.x;
   const int RG = RINGC ? RINGC : a.ring;
   const int RG_LOG = RINGC ? (RINGC == 2 ? 1 : RINGC == 4 ? 2 : RINGC == 8 ? 3 : 4) : (31 - __clz(a.ring));
@@ -349,6 +355,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
   const size_t tape_step = (size_t)a.C * R * NT;
   // the lane that re-issues tape copies sits in a middle warp: the first and last warps already wait for ghost rows
   const int refill_tid = ((NT / 32) / 2) * 32;
+  const bool seed_warp = __any_sync(0xffffffffu, pc0 >= 0);
   const bool plain_warp = !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || pc0 >= 0 || tid == refill_tid ||
                                                        (GRADX && a.grad_x && m1 != 0u));
 
@@ -365,13 +372,13 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
     const int toff = CHAIN ? a.t_off : 0;
     auto stage_seeds = [&](int blk) {   // seeds of time block blk: dLoss/d(raw probe value)
       const int t0 = blk * TB, n = min(TB, a.T - t0);
-      float* dst = ss + (blk & 1) * TB * a.n_prb;
+      float* dst = ss + (blk & 1) * TB;               // ss: [n_prb][2*TB], a ring of 2*TB seeds per probe
       for (int i = tid; i < n * a.n_prb; i += NT) {
         int p = i % a.n_prb;
         size_t o = ((size_t)b * Tst + toff + t0 + i / a.n_prb) * a.n_prb + p;
         float g = a.grad_probe[o];
         if (a.prb_sq[p]) g *= 2.f * a.probe_raw[o];   // probe.py:27
-        dst[i] = g;
+        dst[p * (2 * TB) + i / a.n_prb] = g;
       }
     };
     auto flush_gx = [&](int blk) {
@@ -387,14 +394,24 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
     // load and a compile-time unrolled select; further probes of the same thread go through the general loop.
     auto add_seeds = [&](float (&P)[R][4], int t) {
       if (pc0 >= 0) {
-        const float* srow = ss + (t & (2 * TB - 1)) * a.n_prb;
-        patch_fma_cell<R>(P, k3, pc0, srow[pi0]);
+        const float* srow = ss + (t & (2 * TB - 1));
+        patch_fma_cell<R>(P, k3, pc0, srow[pi0 * (2 * TB)]);
         if (more_probes) {
           for (int p = pi0 + 1; p < a.n_prb; ++p)
-            if (pown[p] == L.lt) patch_fma_cell<R>(P, k3, pcell[p], srow[p]);
+            if (pown[p] == L.lt) patch_fma_cell<R>(P, k3, pcell[p], srow[p * (2 * TB)]);
         }
       }
     };
+    // In the step: the seed of my first probe is fetched at the top of the step and added with predicated FMAs (no branch
+    // tree on the owning warp's path); further probes of the same thread take the general route.
+    auto add_more_seeds = [&](float (&P)[R][4], int t) {
+      if (more_probes) {
+        const float* srow = ss + (t & (2 * TB - 1));
+        for (int p = pi0 + 1; p < a.n_prb; ++p)
+          if (pown[p] == L.lt) patch_fma_cell<R>(P, k3, pcell[p], srow[p * (2 * TB)]);
+      }
+    };
+    const float* seed0 = ss + pi0 * (2 * TB);
     if (tid == 0) {   // prime the tape ring
       for (int s = 0; s < RG && s < a.T; ++s) {
         unsigned slot = (it_global + s) & (RG - 1);
@@ -445,6 +462,8 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
       long long c0 = clock64(), c1 = 0, c2 = 0, c3 = 0, c4 = 0;
 #endif
       if (!PLAIN) L.acquire_ghosts();
+      float sv0 = 0.f;
+      if (!PLAIN && SEED_PRED && seed_warp && t > 0) sv0 = pc0 >= 0 ? seed0[(t - 1) & (2 * TB - 1)] : 0.f;
 #ifdef WT_DEBUG_CLOCK
       c1 = clock64();
 #endif
@@ -462,7 +481,11 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
 #pragma unroll
             for (int k = 0; k < 4; ++k) pr[r][k] = wt_update(k1[r][k], k3[r][k], cu[r][k], pr[r][k], lap[r][k]);
           if (!CHAIN || t > 0) {
-            if (!PLAIN) add_seeds(pr, t - 1);
+            if (!PLAIN && SEED_PRED && seed_warp) {
+              patch_fma_pred<R>(pr, k3, pc0, sv0);
+              add_more_seeds(pr, t - 1);
+            }
+            if (!PLAIN && !SEED_PRED) add_seeds(pr, t - 1);
             L.template publish<PLAIN>(pitch, fld, PAR ^ 1, pr);
           }
         }
