@@ -53,6 +53,8 @@ extern "C" {
 #define WT_F_NEED_GRAD_B 8u     /* the tape must allow grad w.r.t. the damping field in linear mode      */
 #define WT_F_NO_SPECIALIZE 16u  /* on-chip path: run the generic kernels, not a shape-specialised instantiation
                                    (A/B measurements; results are bitwise identical either way)            */
+#define WT_F_NO_PLAIN_WARPS 32u /* on-chip path (linear cell): every warp runs the general instantiation of the time step, also
+                                   the warps without ghost-row, source, probe or refill duties (A/B; bitwise identical) */
 
 /* wt_plan.path */
 #define WT_PATH_STREAM 0    /* one launch per time step, fields live in HBM                     */

@@ -1142,3 +1142,30 @@ def test_float64_config2_and_config4(float64_default):
     m32 = _vowel_model(0.1, 1.0, -30.0)
     out32 = m32(x4.float())
     assert rel_l2(out32.detach().cpu().numpy(), out4.detach().cpu().numpy()) < max(1e-5, 3 * rel_l2(g4["out_f32"], g4["out_f64"]))
+
+
+@pytest.mark.parametrize("case", ["vowel_b64", "vowel_b6", "lens_b1"])
+def test_plain_warp_step_matches_general_step(case, monkeypatch):
+    """The on-chip kernels run warps without special duties (ghost-row exchange, source, probe, tape refill, inactive lanes)
+    through a second, branch-free instantiation of the time step (csrc/wt_resident.cu: PLAIN).  WT_F_NO_PLAIN_WARPS sends every
+    warp through the general one: probes, rho.grad and x.grad must agree bit for bit."""
+    if case == "vowel_b64":
+        build, (B, T) = _vowel_model, (64, 130)
+    elif case == "vowel_b6":
+        build, (B, T) = _vowel_model, (6, 150)
+    else:
+        build, (B, T) = (lambda: _lens_model(0.5)), (1, 150)
+    x0 = wo.synthetic_vowels(B, T)
+    w = torch.tensor(np.random.RandomState(11).rand(B, T, 3), dtype=torch.float32, device=DEV)
+    res = []
+    for noplain in ("1", "0"):
+        monkeypatch.setenv("WT_RES_NOPLAIN", noplain)
+        m = build()
+        x = torch.tensor(x0, device=DEV, requires_grad=True)
+        out = m(x)
+        (out * w).sum().backward()
+        res.append((out.detach().clone(), m.cell.geom.rho.grad.clone(), x.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
+    if case != "lens_b1":      # line source: dLoss/dx is summed with shared-memory atomics in arrival order
+        assert torch.equal(res[0][2], res[1][2])

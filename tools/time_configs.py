@@ -24,9 +24,22 @@ def report(name, m, x, labels, cells, Nx, Ny, nl=(0, 0, 0)):
         o = m(x); torch.nn.functional.cross_entropy(wt.utils.normalize_power(o.sum(1)), labels).backward(); m.zero_grad(set_to_none=True)
     tf, tb = tm(fwd), tm(full)
     print(f"| {name} | {'on-chip' if plan.path else 'stream'} C={plan.cluster} R={plan.rows_per_thread} | {tf:.3f} | {cells/tf/1e6:.1f} | {tb:.3f} | {cells/tb/1e6:.1f} |", flush=True)
+def report_graphed(name, m, x, labels, cells):
+    """The whole training iteration (forward, loss head, adjoint, Adam, constrain) replayed from a CUDA graph: what is left when
+    the host launch latency of the ~60 small launches is taken out (it dominates the eager numbers of the small configs)."""
+    from wavetorch_b200.graph import GraphedTrainStep
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+    step = GraphedTrainStep(m, opt, lambda o, y: torch.nn.functional.cross_entropy(wt.utils.normalize_power(o.sum(1)), y), x, labels)
+    t = tm(lambda: step(x, labels), n=20)
+    print(f"| {name}, training iteration from a CUDA graph | | | | {t:.3f} | {cells/t/1e6:.1f} |", flush=True)
 print("| config | plan | fwd ms | fwd Gcell/s | fwd+bwd ms | fwd+bwd Gcell/s |\n|---|---|---|---|---|---|")
 m = _lens_model(0.5); x = torch.tensor(wo.propagate_waveform(500), device="cuda")
 report("1/2 lens 151x151 B=1 T=500", m, x, torch.tensor([2], device="cuda"), 151 * 151 * 500, 151, 151)
+report_graphed("1/2 lens 151x151 B=1 T=500", _lens_model(0.5), x, torch.tensor([2], device="cuda"), 151 * 151 * 500)
+if os.environ.get("ONLY_SMALL"):
+    m = _vowel_model(); x = torch.tensor(wo.synthetic_vowels(8, 1000), device="cuda")
+    report_graphed("3 vowel 150x100 B=8 T=1000", m, x, torch.arange(8, device="cuda") % 3, 8 * 1000 * 15000)
+    sys.exit(0)
 for B, T in ((64, 1000), (8, 1000), (64, 5469)):
     m = _vowel_model(); x = torch.tensor(wo.synthetic_vowels(B, T), device="cuda")
     report(f"3 vowel 150x100 B={B} T={T}", m, x, torch.arange(B, device="cuda") % 3, B * T * 15000, 150, 100)

@@ -16,6 +16,7 @@ WT_F_FORCE_STREAM = 2
 WT_F_FORCE_RESIDENT = 4
 WT_F_NEED_GRAD_B = 8
 WT_F_NO_SPECIALIZE = 16
+WT_F_NO_PLAIN_WARPS = 32
 WT_PATH_STREAM = 0
 WT_PATH_RESIDENT = 1
 
@@ -119,6 +120,8 @@ def make_problem(Nx, Ny, B, T, n_src, n_prb, dt, h, b0=0.0, uth=0.0, c_nl=0.0, f
     p.Nx, p.Ny, p.B, p.T, p.n_src, p.n_prb = int(Nx), int(Ny), int(B), int(T), int(n_src), int(n_prb)
     if os.environ.get("WT_RES_NOSPEC", "0") == "1":     # A/B switch: generic instead of shape-specialised kernels
         flags |= WT_F_NO_SPECIALIZE
+    if os.environ.get("WT_RES_NOPLAIN", "0") == "1":    # A/B switch: no plain-warp instantiation of the time step
+        flags |= WT_F_NO_PLAIN_WARPS
     p.flags, p.device = int(flags), int(device)
     p.dt, p.h, p.b0, p.uth, p.c_nl = float(dt), float(h), float(b0), float(uth), float(c_nl)
     p.cluster = int(os.environ.get("WT_CLUSTER", cluster))

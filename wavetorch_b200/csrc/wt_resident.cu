@@ -38,7 +38,7 @@ namespace wt {
 // CKPT: the checkpoint-and-recompute instantiation -- the launch covers steps [t_off, t_off + T) of longer sequences, can
 // start from a stored snapshot of the register patches and stores snapshots every snap_every steps (a multiple of TB) on
 // its way; the common kernels carry none of that code.
-template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false, bool CKPT = false>
+template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false, bool CKPT = false, bool NOPLAIN = false>
 __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_blocks<R>(NTC)) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
 #ifdef WT_DEBUG_CLOCK
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
   const int my_poff = (plane_lane < a.n_prb) ? poff[plane_lane] : -1;
   // a warp without special duties: all lanes own cells, none borders another CTA, owns a source, samples a probe or has to
   // publish interior cells for a probe lane; and the FIELDS / CKPT instantiations keep to the general step
-  const bool plain_warp = !FIELDS && !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || L.pub_all || m1 != 0u || my_poff >= 0);
+  const bool plain_warp = !FIELDS && !NOPLAIN && !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || L.pub_all || m1 != 0u || my_poff >= 0);
   const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;       // my first row inside a slab buffer
   const size_t tape_step = (size_t)a.C * R * NT;        // float4 per time step of one sample
   const size_t plane = (size_t)a.Nx * a.Ny;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
 // CHAIN: the checkpoint-and-recompute instantiation -- the launch covers the reverse steps of the segment [t_off, t_off+T)
 // of longer sequences; the pair (P_{t-1}, P_t) at the segment boundary is handed from launch to launch through a.chain
 // in the register layout (no lambda <-> P conversion, no division), and the per-cluster gradient partials accumulate.
-template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1, int RINGC = 0, bool CHAIN = false>
+template <int R, int PITCH = 0, int NTC = 0, int GRADX = 1, int RINGC = 0, bool CHAIN = false, bool NOPLAIN = false>
 __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_blocks<R>(NTC)) k_res_adj(ResArgs a) {
   constexpr bool EARLY = R <= 2;   // see the step body
   constexpr bool SEED_PRED = R >= 4;   // big patches: probe seeds fetched ahead and added with predicated FMAs (R = 5: adjoint -3 %; slower at R = 2)
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
   // the lane that re-issues tape copies sits in a middle warp: the first and last warps already wait for ghost rows
   const int refill_tid = ((NT / 32) / 2) * 32;
   const bool seed_warp = __any_sync(0xffffffffu, pc0 >= 0);
-  const bool plain_warp = !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || pc0 >= 0 || tid == refill_tid ||
+  const bool plain_warp = !NOPLAIN && !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || pc0 >= 0 || tid == refill_tid ||
                                                        (GRADX && a.grad_x && m1 != 0u));
 
   float G[R][4];
@@ -948,6 +948,11 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
     WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, false, 0, 0, false, true>, plan, plan.smem_fwd, a, st)));
     return WT_OK;
   }
+  if (!a.fields && (a.flags & WT_F_NO_PLAIN_WARPS)) {   // A/B and test switch: every warp through the general step (generic kernels)
+    if (a.tape) { WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, true, 0, 0, false, false, true>, plan, plan.smem_fwd, a, st))); }
+    else { WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_fwd<R, false, 0, 0, false, false, true>, plan, plan.smem_fwd, a, st))); }
+    return WT_OK;
+  }
   if (!a.fields && !(a.flags & WT_F_NO_SPECIALIZE)) {
 #define WT_SPEC_F(R_, P_, N_, G_)                                                                       \
     if (plan.rows_per_thread == R_ && a.pitch == P_ && plan.threads == N_) {                              \
@@ -1040,7 +1045,11 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
     return WT_OK;
   }
   bool launched = false;
-  if (!(a.flags & WT_F_NO_SPECIALIZE)) {
+  if (a.flags & WT_F_NO_PLAIN_WARPS) {
+    WT_DISPATCH_R(plan.rows_per_thread, WT_TRY(launch_cluster(k_res_adj<R, 0, 0, 1, 0, false, true>, plan, plan.smem_bwd, a, st)));
+    launched = true;
+  }
+  if (!launched && !(a.flags & WT_F_NO_SPECIALIZE)) {
 #define WT_SPEC_A(R_, P_, N_, G_)                                                                               \
     if (!launched && plan.rows_per_thread == R_ && a.pitch == P_ && plan.threads == N_ && a.ring == G_) {         \
       if (a.grad_x) WT_TRY(launch_cluster(k_res_adj<R_, P_, N_, 1, G_>, plan, plan.smem_bwd, a, st));             \
