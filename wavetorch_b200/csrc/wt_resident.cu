@@ -634,8 +634,8 @@ static int max_threads_for(int R) {
   switch (R) {
     case 1: return 512;
     case 2: return 512;
-    case 3: return 640;
-    case 4: return 512;
+    case 3: return 384;
+    case 4: return 384;
     case 5: return 384;
     case 6: return 320;
     case 8: return 256;
@@ -694,6 +694,7 @@ static int active_clusters(K kernel, int C, int threads, size_t smem) {
 #define WT_SPEC_SHAPES(X)                                                                                              \
   X(5, 104, 384, 4)  /* 150x100, C=2: study/example.yml geometry at B >= 64 (BASELINE config 3, bench.py)          */ \
   X(2, 104, 256, 16) /* 150x100, C=8: example.yml at its own batch_size 6; config 3 sharded 8 per GPU             */ \
+  X(3, 104, 352, 4)  /* 150x100, C=4: config 3 sharded 32 per GPU (64 waveforms over 2 GPUs)                       */ \
   X(2, 144, 320, 8)  /* 140x140, C=8: study/linear/linear.yml (batch_size 9)                                      */ \
   X(2, 156, 384, 8)  /* 151x151, C=8: study/propagate.py, study/optimize_lens.py (BASELINE configs 1-2)           */
 
@@ -817,8 +818,10 @@ bool resident_plan(const wt_problem* p, const cudaDeviceProp& prop, bool need_ad
         // step of one CTA with Hc rows of 100 cells):  t = a_R + b_R * Hc.  The fixed part a_R is the latency chain of one
         // thread's patch plus the step barrier (small patches win when there are SMs to spread over), the slope b_R the
         // issue-bound rate (big patches win when every SM is busy).  score = 1 / (waves * t).
-        static const double aR[9] = {0, 0.57, 0.65, 1.70, 0.98, 1.30, 1.30, 0, 1.275};
-        static const double bR[9] = {0, 0.031, 0.0185, 0.004, 0.017, 0.0092, 0.0098, 0, 0.0104};
+        // (refitted at the end of round 2: R = 3, 4 are compiled for 384 threads = 168 registers -- at 640 / 512 threads they
+        //  spilled inside the loop -- and the R = 5 step barely depends on the rows of a CTA any more)
+        static const double aR[9] = {0, 0.57, 0.50, 0.925, 0.983, 1.50, 1.30, 0, 1.275};
+        static const double bR[9] = {0, 0.031, 0.0216, 0.0082, 0.0086, 0.0015, 0.0098, 0, 0.0104};
         const double t = aR[R] + bR[R] * Hc * (P4 / 25.0) * (per_sm > 1 ? per_sm : 1);
         score = 1.0 / ((double)waves * t);
         score *= 1.0 - 1e-3 * C;      // ties: the smaller cluster

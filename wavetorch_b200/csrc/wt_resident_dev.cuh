@@ -320,7 +320,7 @@ template <int R>
 constexpr int res_max_threads() {
   // R <= 2: 512 threads (128 registers) rather than the 1024 / 768 a small patch would allow: at 64 / 85 registers the
   // adjoint spills inside the time loop, and decompositions that would need more threads pick a larger R anyway
-  return R <= 2 ? 512 : R == 3 ? 640 : R == 4 ? 512 : R == 5 ? 384 : R == 6 ? 320 : 256;
+  return R <= 2 ? 512 : R == 3 ? 384 : R == 4 ? 384 : R == 5 ? 384 : R == 6 ? 320 : 256;
 }
 
 // Minimum CTAs per SM a shape-specialised instantiation is compiled for.  Two CTAs of 40 rows per SM (C = 4, R = 5, 224
