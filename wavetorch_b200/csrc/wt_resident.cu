@@ -695,6 +695,7 @@ static int active_clusters(K kernel, int C, int threads, size_t smem) {
   X(5, 104, 384, 4)  /* 150x100, C=2: study/example.yml geometry at B >= 64 (BASELINE config 3, bench.py)          */ \
   X(2, 104, 256, 16) /* 150x100, C=8: example.yml at its own batch_size 6; config 3 sharded 8 per GPU             */ \
   X(3, 104, 352, 4)  /* 150x100, C=4: config 3 sharded 32 per GPU (64 waveforms over 2 GPUs)                       */ \
+  X(2, 104, 352, 8)  /* 150x100, C=6, R=2: config 3 sharded 16 per GPU (64 waveforms over 4 GPUs)                   */ \
   X(2, 144, 320, 8)  /* 140x140, C=8: study/linear/linear.yml (batch_size 9)                                      */ \
   X(2, 156, 384, 8)  /* 151x151, C=8: study/propagate.py, study/optimize_lens.py (BASELINE configs 1-2)           */
 
