@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
         d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3; d[4] = c4; d[5] = c5; d[6] = clock64(); d[7] = PLAIN;
       }
 #endif
-      __syncthreads();
+      step_barrier(NT);
     };
     using P0 = std::integral_constant<int, 0>;
     using P1 = std::integral_constant<int, 1>;
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
         d[0] = c0; d[1] = c1; d[2] = c2; d[3] = c3; d[4] = c4; d[5] = 0; d[6] = clock64(); d[7] = PLAIN;
       }
 #endif
-      __syncthreads();
+      step_barrier(NT);
       if (!PLAIN && tid == refill_tid && it + RG < a.T) {   // every thread has read this slot: refill it RG steps ahead
         mbar_expect_tx(full + slot, stage_bytes);
         bulk_g2s(ring + slot * R * NT, tape_b + (size_t)(t - RG) * tape_step, stage_bytes, full + slot);

@@ -86,6 +86,12 @@ __device__ __forceinline__ void st_stream(float4* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Step barrier of the time loops.  The plain and the general instantiation of a step are different instruction streams, so
+// the warps of a CTA reach the barrier at different program counters: that is outside the contract of __syncthreads()
+// (compute-sanitizer synccheck flags it) but exactly what the PTX barrier with an explicit thread count is for -- barrier 0,
+// all NT threads, each warp convergent (.aligned), as in any warp-specialised kernel.
+__device__ __forceinline__ void step_barrier(int nt) { asm volatile("barrier.cta.sync.aligned 0, %0;" ::"r"(nt) : "memory"); }
+
 // ---- cluster ghost-row exchange -------------------------------------------------------------------
 // Ghost rows travel with st.async: a 16-byte store into the neighbour CTA's shared memory that also counts
 // its bytes on an mbarrier there (complete_tx).  The receiver waits on its own mbarrier only, so the time loop
