@@ -82,8 +82,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+#ifndef WT_ST_POLICY
+// Cache policy of the tape stores, measured in same-box A/Bs at config 3 (forward with tape, ms): .cg 0.757 / default (.wb) 0.758 /
+// .cs (evict-first, used until the end of round 2) 0.813 / .L1::no_allocate 0.925 on one box, 0.842 / 0.842 / 0.930 / 0.926 on a slower one.
+#define WT_ST_POLICY ".cg"
+#endif
 __device__ __forceinline__ void st_stream(float4* p, float4 v) {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  asm volatile("st.global" WT_ST_POLICY ".v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // Step barrier of the time loops.  The plain and the general instantiation of a step are different instruction streams, so
