@@ -893,13 +893,22 @@ static int launch_cluster(K kernel, const wt_plan& plan, size_t smem, const ResA
   cfg.blockDim = dim3(plan.threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = plan.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static const int sched = [] {   // WT_CLUSTER_SCHED=spread|lb: cluster scheduling policy preference (A/B measurements)
+    const char* e = getenv("WT_CLUSTER_SCHED");
+    return !e ? 0 : (e[0] == 's' ? 1 : 2);
+  }();
+  if (sched) {
+    attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+    attr[1].val.clusterSchedulingPolicyPreference = sched == 1 ? cudaClusterSchedulingPolicySpread : cudaClusterSchedulingPolicyLoadBalancing;
+    cfg.numAttrs = 2;
+  }
   WT_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
   return WT_OK;
 }
