@@ -1169,3 +1169,15 @@ def test_plain_warp_step_matches_general_step(case, monkeypatch):
     assert torch.equal(res[0][1], res[1][1])
     if case != "lens_b1":      # line source: dLoss/dx is summed with shared-memory atomics in arrival order
         assert torch.equal(res[0][2], res[1][2])
+
+
+def test_planner_choices_for_config3_shards():
+    """The decompositions the planner picks for BASELINE config 3 and its batch shards (64 waveforms on 1 / 2 / 4 / 8 GPUs):
+    they are what the cost model in csrc/wt_resident.cu was fitted for (profiles/r2_sweeps.md) and what the shape-specialised
+    instantiations exist for."""
+    want = {64: (2, 5, 384), 32: (4, 3, 352), 16: (6, 2, 352), 8: (8, 2, 256)}
+    for B, (C, R, threads) in want.items():
+        plan = _lib.query_plan(_lib.make_problem(150, 100, B, 1000, 1, 3, 1.0, 1.4283556979968262, flags=_lib.WT_F_ZERO_INIT))
+        assert plan.path == _lib.WT_PATH_RESIDENT
+        assert (plan.cluster, plan.rows_per_thread, plan.threads) == (C, R, threads), (B, plan.cluster, plan.rows_per_thread, plan.threads)
+        assert plan.n_clusters == B
