@@ -15,6 +15,10 @@
 //             fetched by cp.async.bulk into a shared-memory ring ahead of use)
 // The step bodies are kept small on purpose: they are fetched 2T times per sample and everything inlined into them --
 // also code that a branch skips -- costs instruction-cache bandwidth.
+// Each kernel carries TWO instantiations of its step: the general one, and a PLAIN one for warps in which no lane waits for
+// or pushes ghost rows, owns a source or a probe, refills the tape ring or is inactive -- most warps of a CTA.  The choice is
+// made once per sample by a warp-uniform branch around the whole time loop; all warps meet at the same barrier 0 every step.
+// Slab buffers: plane layout with a per-run skew, see wt_resident_dev.cuh (every access is one conflict-free wavefront).
 //
 // Reference semantics: wavetorch/rnn.py:36-70, cell.py:12-17, cell.py:27-44, operators.py:5-11,
 // source.py:15-22, probe.py:14-27.
