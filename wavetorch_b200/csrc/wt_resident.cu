@@ -42,7 +42,7 @@ namespace wt {
 // CKPT: the checkpoint-and-recompute instantiation -- the launch covers steps [t_off, t_off + T) of longer sequences, can
 // start from a stored snapshot of the register patches and stores snapshots every snap_every steps (a multiple of TB) on
 // its way; the common kernels carry none of that code.
-template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false, bool CKPT = false, bool NOPLAIN = false>
+template <int R, bool TAPE, int PITCH = 0, int NTC = 0, bool FIELDS = false, bool CKPT = false, bool NOPLAIN = false, bool TMAST = false>
 __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_blocks<R>(NTC)) k_res_fwd(ResArgs a) {
   extern __shared__ float4 smem4[];
 #ifdef WT_DEBUG_CLOCK
@@ -55,10 +55,13 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
   float* ps = xs + 2 * TB;                             // [n_prb][2*TB]: a ring of 2*TB samples per probe
   int* poff = reinterpret_cast<int*>(ps + 2 * TB * a.n_prb);  // [n_prb] offset into a slab buffer, or -1
   uint64_t* bars = reinterpret_cast<uint64_t*>(poff + a.n_prb + (a.n_prb & 1));
+  // TMAST: the tape rows of a step are staged in shared memory (three buffers) and leave through ONE TMA bulk store per step
+  float4* tst = TMAST ? reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(bars + 4) + 127) & ~(uintptr_t)127) : nullptr;
 
   Lane<R> L;
   L.init(a, fld, bars);
   const int tid = L.tid, NT = NTC ? NTC : blockDim.x;
+  const int store_tid = ((NT / 32) / 2) * 32;   // TMAST: the lane that issues the bulk stores (its warp runs the general step)
   float k1[R][4], k3[R][4];
   load_coef<R>(a, L.active, L.gi0, L.j0, k1, k3);
   unsigned m1, m2;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
   const int my_poff = (plane_lane < a.n_prb) ? poff[plane_lane] : -1;
   // a warp without special duties: all lanes own cells, none borders another CTA, owns a source, samples a probe or has to
   // publish interior cells for a probe lane; and the FIELDS / CKPT instantiations keep to the general step
-  const bool plain_warp = !FIELDS && !NOPLAIN && !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || L.pub_all || m1 != 0u || my_poff >= 0);
+  const bool plain_warp = !FIELDS && !NOPLAIN && !__any_sync(0xffffffffu, !L.active || L.edge_up || L.edge_dn || L.pub_all || m1 != 0u || my_poff >= 0 || (TMAST && tid == store_tid));
   const int own = (L.lr0 + 1) * pitch + (L.run + 1) * slab_skew(R, pitch) + L.g;       // my first row inside a slab buffer
   const size_t tape_step = (size_t)a.C * R * NT;        // float4 per time step of one sample
   const size_t plane = (size_t)a.Nx * a.Ny;
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
     const float* rd0 = fld + own;                 // my patch in slab buffer 0 / 1
     const float* rd1 = fld + L.slab + own;
     float* psw = ps + plane_lane * (2 * TB);      // sample ring of this lane's probe (the last n_prb lanes only)
+    int tslot = 0;                                // TMAST: staging buffer of the current step
     // PLAIN: the instantiation for warps without special duties (plain_warp below) carries none of the flag tests and
     // branch regions of the general step -- ghost-row waits and pushes, probe sampling, source injection, inactive lanes.
     // Those cost a warp ~30 instructions and six divergence regions per step even when every one of them is skipped, and
@@ -156,7 +160,13 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
         if (!PLAIN) xv = src_warp ? xs[t & (2 * TB - 1)] : 0.f;   // fetched ahead of the stencil: off the source warp's path
         float lap[R][4];
         patch_laplacian<R>(pitch, cur, cu, lap);
-        if (TAPE && PLAIN) {
+        if (TAPE && TMAST) {
+          float4* dst = tst + tslot * (R * NT) + tid;
+#pragma unroll
+          for (int r = 0; r < R; ++r) dst[r * NT] = make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my rows, visible to the TMA engine after the barrier
+        }
+        if (TAPE && !TMAST && PLAIN) {
           // The tape rows go out BEFORE the update and the publish.  The LSU queue is in order: issued last, the 128-bit
           // tape stores of the warps that finish early sit in front of the rim stores and ghost-row pushes of the warps
           // that finish late -- the ones the step barrier waits for (measured: 700-1200 cycles for an edge warp's publish).
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
 #ifdef WT_DEBUG_CLOCK
         c5 = clock64();
 #endif
-        if (TAPE && !PLAIN) {   // a warp with special duties: its rim stores and pushes are what others wait for, the tape comes last
+        if (TAPE && !TMAST && !PLAIN) {   // a warp with special duties: its rim stores and pushes are what others wait for, the tape comes last
 #pragma unroll
           for (int r = 0; r < R; ++r) st_stream(tape + (size_t)r * NT, make_float4(lap[r][0], lap[r][1], lap[r][2], lap[r][3]));
           tape += tape_step;
@@ -218,6 +228,18 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
       }
 #endif
       step_barrier(NT);
+      if (TAPE && TMAST) {
+        if (!PLAIN && tid == store_tid) {   // every row of this step is staged: one bulk store; the buffer written two steps
+          // from now was read by the store before the previous one, which wait_group.read 1 has seen finish before the NEXT barrier
+          const float4* gdst = a.tape + (((size_t)b * a.T + t) * a.C + L.rank) * R * NT;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(tst + tslot * (R * NT))),
+                       "r"((unsigned)(R * NT * sizeof(float4)))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        tslot = tslot == 2 ? 0 : tslot + 1;
+      }
     };
     using P0 = std::integral_constant<int, 0>;
     using P1 = std::integral_constant<int, 1>;
@@ -258,6 +280,7 @@ __global__ void __launch_bounds__(NTC ? NTC : res_max_threads<R>(), res_min_bloc
     // Every warp executes the same sequence of __syncthreads(); only the instruction stream between them differs.
     if (plain_warp) run(std::true_type{}); else run(std::false_type{});
     L.npub = npub0 + (unsigned)a.T;
+    if (TAPE && TMAST && tid == store_tid) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     L.acquire_ghosts();   // consume the last publish so that no st.async is in flight past this point
     if (my_poff >= 0) psw[(a.T - 1) & (2 * TB - 1)] = fld[(a.T & 1) * L.slab + my_poff];
     __syncthreads();
@@ -694,14 +717,23 @@ static int active_clusters(K kernel, int C, int threads, size_t smem) {
 // that every shared-memory and tape offset of the step body is an immediate (5-14 % on the step).  One entry per plan the
 // planner picks for the grids and batch sizes of the reference's study configs; anything else runs the generic kernels
 // (bitwise the same results: tests/test_gpu_parity.py::test_shape_specialised_kernels_match_generic_ones).
-//   X(R, PITCH, THREADS, RING)
+//   X(R, PITCH, THREADS, RING, TMAST)
+// TMAST = 1: the tape-writing forward of this shape stages the tape rows of a step in shared memory (three buffers) and
+// stores them with ONE TMA bulk copy per step instead of five 128-bit stores per thread.  Measured for the config-3 shape
+// (same-box A/B, forward with tape: 0.859 -> 0.748 ms); WT_FWD_TMAST=0 / 1 overrides the table for A/B measurements.
 #define WT_SPEC_SHAPES(X)                                                                                              \
-  X(5, 104, 384, 4)  /* 150x100, C=2: study/example.yml geometry at B >= 64 (BASELINE config 3, bench.py)          */ \
-  X(2, 104, 256, 16) /* 150x100, C=8: example.yml at its own batch_size 6; config 3 sharded 8 per GPU             */ \
-  X(3, 104, 352, 4)  /* 150x100, C=4: config 3 sharded 32 per GPU (64 waveforms over 2 GPUs)                       */ \
-  X(2, 104, 352, 8)  /* 150x100, C=6, R=2: config 3 sharded 16 per GPU (64 waveforms over 4 GPUs)                   */ \
-  X(2, 144, 320, 8)  /* 140x140, C=8: study/linear/linear.yml (batch_size 9)                                      */ \
-  X(2, 156, 384, 8)  /* 151x151, C=8: study/propagate.py, study/optimize_lens.py (BASELINE configs 1-2)           */
+  X(5, 104, 384, 4, 1)  /* 150x100, C=2: study/example.yml geometry at B >= 64 (BASELINE config 3, bench.py)          */ \
+  X(2, 104, 256, 16, 0) /* 150x100, C=8: example.yml at its own batch_size 6; config 3 sharded 8 per GPU             */ \
+  X(3, 104, 352, 4, 0)  /* 150x100, C=4: config 3 sharded 32 per GPU (64 waveforms over 2 GPUs)                       */ \
+  X(2, 104, 352, 8, 0)  /* 150x100, C=6, R=2: config 3 sharded 16 per GPU (64 waveforms over 4 GPUs)                   */ \
+  X(2, 144, 320, 8, 0)  /* 140x140, C=8: study/linear/linear.yml (batch_size 9)                                      */ \
+  X(2, 156, 384, 8, 0)  /* 151x151, C=8: study/propagate.py, study/optimize_lens.py (BASELINE configs 1-2)           */
+
+static size_t tape_stage_bytes(int R, int threads) { return (size_t)3 * R * threads * 16 + 256; }
+static int fwd_tmast_override() {   // -1: follow the table
+  static const int v = [] { const char* e = getenv("WT_FWD_TMAST"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+  return v;
+}
 
 // Clusters that can be co-resident for both kernels of a decomposition (0 = cannot launch).  Cached per device.
 static int resident_clusters(int device, int R, int C, int threads, size_t smem_fwd, size_t smem_bwd, int pitch, int ring,
@@ -721,10 +753,13 @@ static int resident_clusters(int device, int R, int C, int threads, size_t smem_
   }
   // a shape-specialised instantiation is what will be launched: its register budget (two CTAs per SM for the small ones) counts
   if (specialize) {
-#define WT_SPEC_OCC(R_, P_, N_, G_)                                                                        \
+#define WT_SPEC_OCC(R_, P_, N_, G_, T_)                                                                    \
     if (R == R_ && pitch == P_ && threads == N_) {                                                           \
+      const bool tm = fwd_tmast_override() < 0 ? (T_ != 0) : fwd_tmast_override() != 0;                       \
       int n0 = active_clusters(k_res_fwd<R_, false, P_, N_>, C, threads, smem_fwd);                          \
-      int n1 = active_clusters(k_res_fwd<R_, true, P_, N_>, C, threads, smem_fwd);                           \
+      int n1 = tm ? active_clusters(k_res_fwd<R_, true, P_, N_, false, false, false, true>, C, threads,      \
+                                    smem_fwd + tape_stage_bytes(R_, N_))                                      \
+                  : active_clusters(k_res_fwd<R_, true, P_, N_>, C, threads, smem_fwd);                       \
       nf = n0 < n1 ? n0 : n1;                                                                                \
       if (ring == G_) {                                                                                      \
         int b0 = active_clusters(k_res_adj<R_, P_, N_, 0, G_>, C, threads, smem_bwd);                        \
@@ -971,9 +1006,13 @@ int resident_forward(const wt_problem* p, const wt_plan& plan, const float* c, c
     return WT_OK;
   }
   if (!a.fields && !(a.flags & WT_F_NO_SPECIALIZE)) {
-#define WT_SPEC_F(R_, P_, N_, G_)                                                                       \
+#define WT_SPEC_F(R_, P_, N_, G_, T_)                                                                   \
     if (plan.rows_per_thread == R_ && a.pitch == P_ && plan.threads == N_) {                              \
-      if (a.tape) WT_TRY(launch_cluster(k_res_fwd<R_, true, P_, N_>, plan, plan.smem_fwd, a, st));        \
+      const bool tm = fwd_tmast_override() < 0 ? (T_ != 0) : fwd_tmast_override() != 0;                    \
+      if (a.tape && tm)                                                                                   \
+        WT_TRY(launch_cluster(k_res_fwd<R_, true, P_, N_, false, false, false, true>, plan,               \
+                              plan.smem_fwd + tape_stage_bytes(R_, N_), a, st));                           \
+      else if (a.tape) WT_TRY(launch_cluster(k_res_fwd<R_, true, P_, N_>, plan, plan.smem_fwd, a, st));   \
       else WT_TRY(launch_cluster(k_res_fwd<R_, false, P_, N_>, plan, plan.smem_fwd, a, st));              \
       return WT_OK;                                                                                       \
     }
@@ -1067,7 +1106,7 @@ int resident_backward(const wt_problem* p, const wt_plan& plan, const float* c, 
     launched = true;
   }
   if (!launched && !(a.flags & WT_F_NO_SPECIALIZE)) {
-#define WT_SPEC_A(R_, P_, N_, G_)                                                                               \
+#define WT_SPEC_A(R_, P_, N_, G_, T_)                                                                              \
     if (!launched && plan.rows_per_thread == R_ && a.pitch == P_ && plan.threads == N_ && a.ring == G_) {         \
       if (a.grad_x) WT_TRY(launch_cluster(k_res_adj<R_, P_, N_, 1, G_>, plan, plan.smem_bwd, a, st));             \
       else WT_TRY(launch_cluster(k_res_adj<R_, P_, N_, 0, G_>, plan, plan.smem_bwd, a, st));                      \
